@@ -1,0 +1,218 @@
+/* rdb200.h -- C ABI of the B200-native Reflected-Diffusion sampling hot path.
+ *
+ * Every entry point takes plain device pointers (caller-owned, e.g. torch allocations),
+ * sizes and a cudaStream_t passed as void*; nothing here allocates device memory except
+ * rd_plan_* (host-side bookkeeping only) and nothing synchronises the stream, so all
+ * calls are CUDA-graph capturable.  Return value: 0 on success, otherwise a cudaError_t
+ * (positive) or an RD_E_* code (negative); rd_last_error() gives the message.
+ *
+ * Reference interfaces replaced (all under /root/reference/Reflected-Diffusion):
+ *   rd_reflect_f32            cube.reflect                         cube.py:34-49
+ *   rd_inside_f32             cube.inside                          cube.py:17-31
+ *   rd_score_hk_f32           cube.score_hk                        cube.py:149-193
+ *   rd_philox_normal_f32      torch.randn_like call sites          sampling.py:200,224
+ *   rd_pc_norms / rd_pc_corrector_apply
+ *                             ReflectedLangevinCorrector.update_fn sampling.py:215-233
+ *   rd_pc_predictor_step      ReflectedEulerMaruyamaPredictor.update_fn + RSDE.sde
+ *                                                                  sampling.py:198-207, sde_lib.py:93-101
+ *   rd_cfg_combine_f32        get_cf_score_fn                      models/utils.py:120-138
+ *   rd_plan_* / rd_op         NCSNpp.forward and its layers        models/ncsnpp.py:226-354,
+ *                                                                  models/layerspp.py:67-214, models/layers.py:531-540
+ *   rd_sampler_*              get_pc_sampler / pc_sampler loop     sampling.py:292-339
+ */
+#ifndef RDB200_H
+#define RDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RD_OK 0
+#define RD_E_INVALID (-1)   /* bad argument */
+#define RD_E_UNSUPPORTED (-2)
+#define RD_E_STATE (-3)
+
+const char* rd_last_error(void);
+int rd_version(void);
+/* compute capability major*10+minor of the current device, or negative error */
+int rd_device_cc(void);
+
+/* ---------------------------------------------------------------- cube.* */
+/* out[i] = reflect(x[i]);  n elements, out may alias x. */
+int rd_reflect_f32(const float* x, float* out, size_t n, void* stream);
+/* ok[b] = all(0 <= x[b,:] <= 1) as uint8;  x is [B, D]. */
+int rd_inside_f32(const float* x, uint8_t* ok, size_t B, size_t D, void* stream);
+/* Reflected heat-kernel score.  x, x_orig, out: [B, D];  sigma: [B] device floats, or NULL and
+ * sigma_scalar is used for every sample.  efs / refls / min_cutoff as in the reference; the sums
+ * are pruned to the terms that can change the fp32 result (see csrc/elementwise.cu). */
+int rd_score_hk_f32(const float* x, const float* x_orig, const float* sigma, float sigma_scalar, float* out,
+                    size_t B, size_t D, int efs, int refls, float min_cutoff, void* stream);
+
+/* ---------------------------------------------------------------- noise */
+/* out[0..n) = the N(0,1) stream the fused step kernels draw for (seed, draw). n multiple of 4. */
+int rd_philox_normal_f32(float* out, size_t n, uint64_t seed, uint32_t draw, void* stream);
+
+/* ---------------------------------------------------------------- predictor / corrector */
+/* Per-step scalars live in device tables indexed by *step_ctr (device int32) so that one captured
+ * graph serves every iteration.  Any table pointer may instead be used with step_ctr == NULL,
+ * in which case index 0 is read.  A noise pointer is advanced by (*step_ctr) * noise_step_stride
+ * elements before use, so a pre-generated noise tape can be replayed from inside a captured graph. */
+
+/* partial[blk*2+{0,1}] = sum over the block's samples of ||grad_b||, ||noise_b||.
+ * noise == NULL -> Philox(seed, draw = draw_base + 2*step + 0).  returns number of blocks via *nblk. */
+int rd_pc_norms(const float* grad, const float* noise, float* partial, int* nblk, size_t B, size_t D,
+                uint64_t seed, uint32_t draw_base, const int32_t* step_ctr, size_t noise_step_stride,
+                void* stream);
+/* x_mean = reflect(x + eps*grad); x_out = reflect(x + eps*grad + sqrt(2 eps)*noise),
+ * eps = 2*(snr*nbar/gbar)^2 with nbar,gbar the batch means rebuilt from `partial`.
+ * x_mean_out may be NULL.  stats_out (optional, 3 floats): gbar, nbar, eps. */
+int rd_pc_corrector_apply(const float* x, const float* grad, const float* noise, const float* partial,
+                          int nblk, float snr, float* x_out, float* x_mean_out, float* stats_out, size_t B,
+                          size_t D, uint64_t seed, uint32_t draw_base, const int32_t* step_ctr,
+                          size_t noise_step_stride, void* stream);
+/* x_mean = reflect(x + g^2*score/N) ; x_out = reflect(x_mean_raw + g*sqrt(1/N)*z).
+ * g_table[step] = diffusion coefficient, dt = -1/N (negative), sqrt_dt = sqrt(1/N).
+ * z == NULL -> Philox(seed, draw = draw_base + 2*step + 1).  advance_ctr != 0 -> (*step_ctr)++ after use. */
+int rd_pc_predictor_step(const float* x, const float* score, const float* z, const float* g_table, float dt,
+                         float sqrt_dt, float* x_out, float* x_mean_out, size_t B, size_t D, uint64_t seed,
+                         uint32_t draw_base, int32_t* step_ctr, size_t noise_step_stride, int advance_ctr,
+                         void* stream);
+/* out = (1+w)*s_cond - w*s_uncond ; s is [2B, D] (cond first); w: [B] device or NULL -> w_scalar. */
+int rd_cfg_combine_f32(const float* s, const float* w, float w_scalar, float* out, size_t B, size_t D,
+                       void* stream);
+
+/* ---------------------------------------------------------------- NCSN++ forward as an op plan */
+/* The host (python, mirroring NCSNpp.__init__) lowers the network to a flat list of ops over
+ * device buffers; the library owns only the kernels.  Activations are NHWC bf16. */
+
+enum rd_op_kind {
+  RD_OP_CONV = 1,      /* implicit-GEMM conv / 1x1 on tcgen05 with fused GN+SiLU prologue and epilogue */
+  RD_OP_ATTN_CORE = 2, /* softmax(q k^T / sqrt(C)) v per sample */
+  RD_OP_TEMB = 3,      /* per-sample Dense_0(SiLU(temb)) for every ResBlock */
+  RD_OP_IN_CONV = 4,   /* 3x3 conv C_in(=channels) -> nf from the fp32 state x */
+  RD_OP_OUT_HEAD = 5   /* GN + SiLU + 3x3 conv nf -> channels, CFG combine, fp32 score */
+};
+
+typedef struct rd_conv_src {
+  const void* ptr; /* bf16 NHWC [B2, Hs, Ws, C] */
+  int32_t C;       /* channels of this source (multiple of 64 after padding rules, see pack.py) */
+  int32_t Hs, Ws;  /* stored spatial size; gathered to (H_in, W_in) by nearest mapping */
+} rd_conv_src;
+
+typedef struct rd_op_conv {
+  rd_conv_src src[2];
+  int32_t nsrc;
+  int32_t H_in, W_in;         /* logical input image (after nearest gather)            */
+  int32_t pad;                /* 1: 3x3 pad 1 (output H_in x W_in); 0: pad (0,1,0,1)    */
+  int32_t stride;             /* 1 or 2 (2 only with pad == 0: Downsample)              */
+  int32_t H_out, W_out;
+  int32_t ntaps;              /* 9 (3x3) or 0 (no 3x3 part, 1x1 only)                   */
+  int32_t C_out;              /* N of the GEMM: 64,128,192,256                          */
+  int32_t gn_groups;          /* 0: no GroupNorm/SiLU prologue                          */
+  int32_t gn_silu;            /* 1: SiLU after GN (ResBlock), 0: GN only (attention)    */
+  float gn_eps;
+  const float* gn_gamma;      /* [C_in_total] */
+  const float* gn_beta;
+  const void* w_taps;         /* bf16 packed [chunk][tap][8][C_out][8]  (GN'd operand)  */
+  const void* w_1x1;          /* bf16 packed [chunk][8][C_out][8] applied to RAW input (NIN shortcut) or NULL */
+  int32_t one_by_one_on_gn;   /* 1: the 1x1 weights act on the GN'd operand (attention q/k/v, NIN_3 has gn_groups=0) */
+  const float* bias;          /* [C_out] (sum of all fused biases) */
+  const float* tproj;         /* [B2, tproj_stride] per-sample additive term or NULL */
+  int32_t tproj_stride, tproj_off;
+  const void* residual;       /* bf16 NHWC [B2,H_out,W_out,C_out] identity skip or NULL */
+  float out_scale;            /* 1/sqrt(2) when skip_rescale, else 1 */
+  void* out;                  /* bf16 NHWC [B2,H_out,W_out,C_out] */
+  int32_t B2;                 /* samples (2B under CFG) */
+  int32_t samples_per_cta;    /* chosen by the host planner */
+} rd_op_conv;
+
+typedef struct rd_op_attn {
+  const void* qkv; /* bf16 [B2, T, 3C] (q | k | v) */
+  void* out;       /* bf16 [B2, T, C] */
+  int32_t B2, T, C;
+} rd_op_attn;
+
+typedef struct rd_op_temb {
+  const float* time_table; /* [n_steps, temb_dim] = time_mlp(fourier(log sigma_i)) + label_emb.bias */
+  const float* label_w;    /* [temb_dim, num_classes] label_emb.weight */
+  const float* labels;     /* [B2, num_classes] */
+  const void* dense_w;     /* bf16? no: fp32 [n_out_total, temb_dim] all Dense_0 weights stacked */
+  const float* dense_b;    /* [n_out_total] */
+  float* out;              /* [B2, n_out_total] */
+  const int32_t* step_ctr; /* device step index (NULL -> row 0) */
+  int32_t B2, temb_dim, num_classes, n_out_total;
+} rd_op_temb;
+
+typedef struct rd_op_inconv {
+  const float* x;    /* fp32 [B, C_in, H, W] (NCHW state, C_in small) ; sample b2 reads x[b2 % B] */
+  const float* w;    /* fp32 [C_out, C_in, 3, 3] */
+  const float* bias; /* [C_out] */
+  void* out;         /* bf16 NHWC [B2,H,W,C_out] */
+  int32_t B, B2, C_in, C_out, H, W;
+} rd_op_inconv;
+
+typedef struct rd_op_outhead {
+  const void* h;       /* bf16 NHWC [B2,H,W,C] */
+  const float* gamma;  /* out_norm */
+  const float* beta;
+  const float* w;      /* fp32 [C_img, C, 3, 3] out_conv.weight */
+  const float* bias;   /* [C_img] */
+  const float* cfg_w;  /* [B] guidance weights or NULL */
+  float cfg_w_scalar;
+  float* score;        /* fp32 [B, C_img, H, W] guided score (or [B2,...] raw if cfg == 0) */
+  int32_t B, B2, C, C_img, H, W, groups, cfg;
+  float eps;
+} rd_op_outhead;
+
+typedef struct rd_op {
+  int32_t kind;
+  int32_t _pad;
+  union {
+    rd_op_conv conv;
+    rd_op_attn attn;
+    rd_op_temb temb;
+    rd_op_inconv inconv;
+    rd_op_outhead outhead;
+  } u;
+} rd_op;
+
+typedef struct rd_plan rd_plan;
+int rd_plan_create(rd_plan** out);
+int rd_plan_add(rd_plan* p, const rd_op* op);
+int rd_plan_size(const rd_plan* p);
+int rd_plan_run(rd_plan* p, void* stream);
+/* run ops [first, first+count) -- unit-test entry point for single layers */
+int rd_plan_run_range(rd_plan* p, int first, int count, void* stream);
+int rd_plan_destroy(rd_plan* p);
+/* shared-memory bytes / CTAs a conv op will launch with (planner feedback, also validates the op) */
+int rd_conv_launch_info(const rd_op_conv* op, int* smem_bytes, int* grid, int* rows_alloc);
+
+/* ---------------------------------------------------------------- whole sampler (sampling.py:292-339) */
+typedef struct rd_sampler_desc {
+  rd_plan* forward;        /* guided score: x -> score (reads x, step_ctr via the ops' pointers) */
+  float* x;                /* [B, D] state, updated in place */
+  float* score;            /* [B, D] written by `forward` */
+  float* partial;          /* scratch >= 2*ceil(B/8) floats */
+  const float* g_table;    /* [N] */
+  int32_t* step_ctr;       /* device */
+  const float* noise_tape; /* NULL (Philox) or [(N-1)*2 or (N-1), B, D]: corrector noise then predictor z per step */
+  uint64_t seed;
+  float snr, dt, sqrt_dt;
+  int32_t B, D, n_corrector_steps; /* 0 -> corrector 'none' */
+} rd_sampler_desc;
+typedef struct rd_sampler rd_sampler;
+int rd_sampler_create(const rd_sampler_desc* d, rd_sampler** out);
+/* enqueue iterations [*step_ctr, *step_ctr + n_iter): corrector(s) then predictor, each with one
+ * guided-score evaluation.  use_graph != 0 captures one iteration into a CUDA graph on first use. */
+int rd_sampler_run(rd_sampler* s, int n_iter, int use_graph, void* stream);
+/* number of kernel launches one iteration issues (for bench.py's gpu_launches) */
+int rd_sampler_launches_per_iter(const rd_sampler* s);
+int rd_sampler_destroy(rd_sampler* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDB200_H */

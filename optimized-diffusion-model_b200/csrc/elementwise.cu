@@ -1,0 +1,517 @@
+// elementwise.cu -- HBM-bound kernels of the sampling hot path:
+//   cube.reflect / cube.inside / cube.score_hk, the CFG combine, the Philox noise dump and the
+//   fused Langevin-corrector / Euler-Maruyama-predictor updates (reflection fused in).
+// All are coalesced 128-bit streaming kernels; reductions use warp shuffles + a fixed-order
+// second-stage sum (no atomics => run-to-run deterministic).
+#include "rd_common.h"
+#include "rd_math.cuh"
+
+namespace rd {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local char g_err[512] = "";
+char* err_buf() { return g_err; }
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+// ------------------------------------------------------------------------------------------------
+// cube.reflect : 8 B / element
+__global__ void __launch_bounds__(256) reflect_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n) {
+  const size_t n4 = n >> 2;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // 4 independent 128-bit loads in flight per thread
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld_stream4(x + 4 * (i + u * stride));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u].x = reflect1(v[u].x); v[u].y = reflect1(v[u].y); v[u].z = reflect1(v[u].z); v[u].w = reflect1(v[u].w);
+      st_stream4(out + 4 * (i + u * stride), v[u]);
+    }
+  }
+  for (; i < n4; i += stride) {
+    float4 v = ld_stream4(x + 4 * i);
+    v.x = reflect1(v.x); v.y = reflect1(v.y); v.z = reflect1(v.z); v.w = reflect1(v.w);
+    st_stream4(out + 4 * i, v);
+  }
+  // tail (< 4 elements)
+  size_t t = (n4 << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = reflect1(x[t]);
+}
+
+// cube.inside (cube.py:17-31): one warp per sample
+__global__ void __launch_bounds__(256) inside_kernel(const float* __restrict__ x, uint8_t* __restrict__ ok, size_t B,
+                                                     size_t D) {
+  size_t w = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= B) return;
+  bool good = true;
+  for (size_t j = lane; j < D; j += 32) {
+    float v = x[w * D + j];
+    good = good && (v >= 0.0f) && (v <= 1.0f);  // NaN fails both, like torch
+  }
+  good = __all_sync(0xffffffffu, good);
+  if (lane == 0) ok[w] = good ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cube.score_hk (cube.py:149-193).  Per sample t = sigma^2/2;  t > min_cutoff -> eigenfunction
+// series (_score_hk_ef, cube.py:73-107) else method of images (_score_hk_refl, cube.py:110-146).
+// Same fp32 operation order as the reference; the sums are truncated to the terms that can still
+// change an fp32 accumulator (6 images / min(efs, ceil(sqrt(17/(pi^2 t)))+3)
+// eigenfunctions reproduce the reference's 42 / 20 terms bit for bit in its own implementation).
+constexpr int HK_SPB = 32;      // samples per block
+constexpr int HK_MAX_EFS = 64;  // table capacity per sample
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr float PI2_F = 9.869604401089358f;  // python float pi**2 -> fp32 scalar
+
+struct HkSampleTab {
+  float t[HK_SPB];
+  int nterm[HK_SPB];  // >= 0: eigenfunction branch with that many terms; -1: reflection branch
+};
+
+__device__ __forceinline__ float hk_ef(float x, float x0, const float* __restrict__ eden, const float* __restrict__ enu,
+                                       int K) {
+  const float px = PI_F * x, p0 = PI_F * x0;  // pi * x  (cube.py:94-95)
+  float num = 0.0f, den = 0.0f;
+  for (int k = 1; k <= K; ++k) {
+    const float kf = static_cast<float>(k);
+    float s, c;
+    sincosf(__fmul_rn(px, kf), &s, &c);
+    const float c0 = cosf(__fmul_rn(p0, kf));
+    num = __fadd_rn(num, __fmul_rn(enu[k - 1], __fmul_rn(s, c0)));   // e_num * (sin * cos0)
+    den = __fadd_rn(den, __fmul_rn(eden[k - 1], __fmul_rn(c, c0)));  // e_den * (cos * cos0)
+  }
+  num = __fmul_rn(-2.0f * PI_F, num);                 // - 2 * pi * sum
+  den = __fadd_rn(1.0f, __fmul_rn(2.0f, den));        // 1 + 2 * sum
+  return __fdiv_rn(num, __fadd_rn(den, 1e-12f));
+}
+
+__device__ __forceinline__ float hk_refl(float x, float x0, float t, int nimg) {
+  const float fourt = __fmul_rn(4.0f, t);
+  float num = 0.0f, den = 0.0f;
+  // torch.cat order (cube.py:131-135): all (2m + x) for m ascending, then all (2m - x)
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    for (int m = -nimg; m <= nimg; ++m) {
+      const float r = static_cast<float>(2 * m);
+      const float y = half == 0 ? __fadd_rn(r, x) : __fsub_rn(r, x);
+      const float d = __fsub_rn(y, x0);
+      const float coeff = __fdiv_rn(__fmul_rn(-2.0f, d), fourt);
+      const float e = expf(__fdiv_rn(-__fmul_rn(d, d), fourt));
+      const float term = __fmul_rn(coeff, e);
+      num = __fadd_rn(num, half == 0 ? term : -term);
+      den = __fadd_rn(den, e);
+    }
+  }
+  return __fdiv_rn(num, __fadd_rn(den, 1e-12f));
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) score_hk_kernel(const float* __restrict__ x, const float* __restrict__ x0,
+                                                       const float* __restrict__ sigma, float sigma_scalar,
+                                                       float* __restrict__ out, size_t B, int D, int efs, int refls,
+                                                       float min_cutoff) {
+  __shared__ HkSampleTab tab;
+  __shared__ float e_den[HK_SPB][HK_MAX_EFS];
+  __shared__ float e_num[HK_SPB][HK_MAX_EFS];
+  const size_t s0 = static_cast<size_t>(blockIdx.x) * HK_SPB;
+  const int ns = static_cast<int>(min(static_cast<size_t>(HK_SPB), B - s0));
+
+  if (threadIdx.x < ns) {
+    const float sg = sigma ? sigma[s0 + threadIdx.x] : sigma_scalar;
+    const float t = __fdiv_rn(__fmul_rn(sg, sg), 2.0f);  // sigma ** 2 / 2
+    tab.t[threadIdx.x] = t;
+    int K = -1;
+    if (t > min_cutoff) {  // ef_cond = t > min_cutoff (cube.py:176)
+      // terms beyond this index are < 2^-24 of the leading ones (e^-17) -- +3 safety margin
+      float kk = ceilf(sqrtf(17.0f / (PI2_F * t))) + 3.0f;
+      K = min(efs, static_cast<int>(fminf(kk, static_cast<float>(HK_MAX_EFS))));
+    }
+    tab.nterm[threadIdx.x] = K;
+  }
+  __syncthreads();
+  // hoisted per-(sample,k) exponentials: exp(-t * k^2 * pi^2)  (cube.py:103-104)
+  for (int i = threadIdx.x; i < ns * HK_MAX_EFS; i += blockDim.x) {
+    const int s = i / HK_MAX_EFS, k = i % HK_MAX_EFS + 1;
+    if (k <= tab.nterm[s]) {
+      const float kf = static_cast<float>(k);
+      const float e = expf(__fmul_rn(__fmul_rn(-tab.t[s], __fmul_rn(kf, kf)), PI2_F));
+      e_den[s][k - 1] = e;
+      e_num[s][k - 1] = __fmul_rn(e, kf);
+    }
+  }
+  __syncthreads();
+
+  const int nimg = min(refls, 1);  // images with |m| >= 2 are >= 2 away: exp(-d^2/4t) underflows below 1 ulp
+  const size_t base = s0 * D;
+  const int nelem = ns * D;
+  for (int e = threadIdx.x * VEC; e < nelem; e += blockDim.x * VEC) {
+    const int s = e / D;  // VEC==4 requires D % 4 == 0 so a vector never straddles samples
+    float xv[VEC], x0v[VEC], r[VEC];
+    if (VEC == 4) {
+      float4 a = ld_stream4(x + base + e), b = ld_stream4(x0 + base + e);
+      xv[0] = a.x; xv[1 % VEC] = a.y; xv[2 % VEC] = a.z; xv[3 % VEC] = a.w;
+      x0v[0] = b.x; x0v[1 % VEC] = b.y; x0v[2 % VEC] = b.z; x0v[3 % VEC] = b.w;
+    } else {
+      xv[0] = x[base + e];
+      x0v[0] = x0[base + e];
+    }
+    const int K = tab.nterm[s];
+    const float t = tab.t[s];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r[v] = K >= 0 ? hk_ef(xv[v], x0v[v], e_den[s], e_num[s], K) : hk_refl(xv[v], x0v[v], t, nimg);
+    if (VEC == 4) {
+      st_stream4(out + base + e, make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]));
+    } else {
+      out[base + e] = r[0];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// noise dump: exactly the stream the fused step kernels consume
+__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, size_t nquad, uint64_t seed,
+                                                            uint32_t draw) {
+  size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; q < nquad; q += stride) {
+    float z[4];
+    philox_normal4(seed, draw, q, z);
+    st_stream4(out + 4 * q, make_float4(z[0], z[1], z[2], z[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// classifier-free guidance combine (models/utils.py:120-138): (1 + w) * s_c - w * s_u
+__global__ void __launch_bounds__(256) cfg_combine_kernel(const float* __restrict__ s, const float* __restrict__ w,
+                                                          float w_scalar, float* __restrict__ out, size_t B, size_t D) {
+  const size_t n = B * D;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const float wv = w ? w[i / D] : w_scalar;
+    out[i] = __fsub_rn(__fmul_rn(__fadd_rn(1.0f, wv), s[i]), __fmul_rn(wv, s[n + i]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Langevin corrector, stage 1 (sampling.py:225-226): per-sample L2 norms of grad and noise.
+// One warp per sample, 8 samples per block; each block emits the sum of its samples' norms.
+constexpr int PC_SPB = 8;
+
+__device__ __forceinline__ uint32_t draw_index(uint32_t draw_base, const int32_t* step_ctr, int which) {
+  const int32_t step = step_ctr ? *step_ctr : 0;
+  return draw_base + 2u * static_cast<uint32_t>(step) + static_cast<uint32_t>(which);
+}
+
+__global__ void __launch_bounds__(32 * PC_SPB) pc_norms_kernel(const float* __restrict__ grad,
+                                                               const float* __restrict__ noise,
+                                                               float* __restrict__ partial, size_t B, int D,
+                                                               uint64_t seed, uint32_t draw_base,
+                                                               const int32_t* __restrict__ step_ctr,
+                                                               size_t noise_step_stride) {
+  __shared__ float sg[PC_SPB], sn[PC_SPB];
+  if (noise && step_ctr) noise += static_cast<size_t>(*step_ctr) * noise_step_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t b = static_cast<size_t>(blockIdx.x) * PC_SPB + warp;
+  float g2 = 0.0f, n2 = 0.0f;
+  if (b < B) {
+    const uint32_t draw = draw_index(draw_base, step_ctr, 0);
+    const size_t e0 = b * D;
+    // D % 4 == 0 is validated on the host when Philox noise is used (quads must not straddle tensors' ends)
+    for (int j = lane * 4; j < D; j += 128) {
+      if (j + 3 < D && (((e0 + j) & 3) == 0)) {
+        float4 g = *reinterpret_cast<const float4*>(grad + e0 + j);
+        float z[4];
+        if (noise) {
+          float4 nz = *reinterpret_cast<const float4*>(noise + e0 + j);
+          z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
+        } else {
+          philox_normal4(seed, draw, (e0 + j) >> 2, z);
+        }
+        g2 += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+        n2 += z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3];
+      } else {
+        for (int u = j; u < min(j + 4, D); ++u) {  // ragged tail / unaligned (tape mode only)
+          const float g = grad[e0 + u], z = noise[e0 + u];
+          g2 += g * g;
+          n2 += z * z;
+        }
+      }
+    }
+  }
+  g2 = warp_sum(g2);
+  n2 = warp_sum(n2);
+  if (lane == 0) {
+    sg[warp] = (b < B) ? sqrtf(g2) : 0.0f;
+    sn[warp] = (b < B) ? sqrtf(n2) : 0.0f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.0f, c = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PC_SPB; ++i) { a += sg[i]; c += sn[i]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = c;
+  }
+}
+
+// fixed-order reduction of the per-block partials by one warp; every block recomputes it (a few KB from L2)
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, float& gsum, float& nsum) {
+  const int lane = threadIdx.x & 31;
+  float a = 0.0f, c = 0.0f;
+  for (int i = lane; i < nblk; i += 32) {
+    a += partial[2 * i];
+    c += partial[2 * i + 1];
+  }
+  gsum = warp_sum(a);
+  nsum = warp_sum(c);
+}
+
+// Langevin corrector, stage 2 (sampling.py:227-231)
+__global__ void __launch_bounds__(256) pc_corrector_apply_kernel(
+    const float* __restrict__ x, const float* __restrict__ grad, const float* __restrict__ noise,
+    const float* __restrict__ partial, int nblk, float snr, float* __restrict__ x_out, float* __restrict__ x_mean_out,
+    float* __restrict__ stats_out, size_t B, size_t n, uint64_t seed, uint32_t draw_base,
+    const int32_t* __restrict__ step_ctr, size_t noise_step_stride) {
+  __shared__ float s_step, s_noise_c;
+  if (noise && step_ctr) noise += static_cast<size_t>(*step_ctr) * noise_step_stride;
+  if (threadIdx.x < 32) {
+    float gsum, nsum;
+    reduce_partials(partial, nblk, gsum, nsum);
+    if (threadIdx.x == 0) {
+      const float gbar = gsum / static_cast<float>(B), nbar = nsum / static_cast<float>(B);
+      const float r = __fdiv_rn(__fmul_rn(snr, nbar), gbar);      // target_snr * noise_norm / grad_norm
+      const float step = __fmul_rn(__fmul_rn(r, r), 2.0f);        // (...) ** 2 * 2 * alpha(=1)
+      s_step = step;
+      s_noise_c = sqrtf(__fmul_rn(step, 2.0f));                   // sqrt(step_size * 2)
+      if (stats_out && blockIdx.x == 0) { stats_out[0] = gbar; stats_out[1] = nbar; stats_out[2] = step; }
+    }
+  }
+  __syncthreads();
+  const float step = s_step, nc = s_noise_c;
+  const uint32_t draw = draw_index(draw_base, step_ctr, 0);
+  const size_t n4 = n >> 2;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + 4 * i);
+    const float4 gv = *reinterpret_cast<const float4*>(grad + 4 * i);
+    float z[4];
+    if (noise) {
+      const float4 nz = ld_stream4(noise + 4 * i);
+      z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
+    } else {
+      philox_normal4(seed, draw, i, z);
+    }
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    float xm[4], xn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float m = __fadd_rn(xs[u], __fmul_rn(step, gs[u]));  // x_mean = x + step * grad
+      xn[u] = reflect1(__fadd_rn(m, __fmul_rn(nc, z[u])));       // x = x_mean + sqrt(2 step) * noise
+      xm[u] = reflect1(m);
+    }
+    *reinterpret_cast<float4*>(x_out + 4 * i) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    if (x_mean_out) *reinterpret_cast<float4*>(x_mean_out + 4 * i) = make_float4(xm[0], xm[1], xm[2], xm[3]);
+  }
+  // scalar tail (tape mode only; Philox mode requires n % 4 == 0)
+  size_t t = (n4 << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < n) {
+    const float m = __fadd_rn(x[t], __fmul_rn(step, grad[t]));
+    x_out[t] = reflect1(__fadd_rn(m, __fmul_rn(nc, noise[t])));
+    if (x_mean_out) x_mean_out[t] = reflect1(m);
+  }
+}
+
+// Euler-Maruyama predictor on the reverse reflected VE-SDE (sampling.py:198-207, sde_lib.py:93-101,135-140):
+//   drift = 0 - g^2 * score ; x_mean = x + drift * dt ; x = x_mean + (g * sqrt(-dt)) * z ; reflect both
+__global__ void __launch_bounds__(256) pc_predictor_kernel(const float* __restrict__ x, const float* __restrict__ score,
+                                                           const float* __restrict__ zt, const float* __restrict__ g_table,
+                                                           float dt, float sqrt_dt, float* __restrict__ x_out,
+                                                           float* __restrict__ x_mean_out, size_t n, uint64_t seed,
+                                                           uint32_t draw_base, const int32_t* __restrict__ step_ctr,
+                                                           size_t noise_step_stride) {
+  const int32_t step = step_ctr ? *step_ctr : 0;
+  if (zt) zt += static_cast<size_t>(step) * noise_step_stride;
+  const float g = g_table[step];
+  const float g2 = __fmul_rn(g, g);
+  const float gz = __fmul_rn(g, sqrt_dt);
+  const uint32_t draw = draw_base + 2u * static_cast<uint32_t>(step) + 1u;
+  const size_t n4 = n >> 2;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + 4 * i);
+    const float4 sv = *reinterpret_cast<const float4*>(score + 4 * i);
+    float z[4];
+    if (zt) {
+      const float4 nz = ld_stream4(zt + 4 * i);
+      z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
+    } else {
+      philox_normal4(seed, draw, i, z);
+    }
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
+    float xm[4], xn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float drift = -__fmul_rn(g2, ss[u]);
+      const float m = __fadd_rn(xs[u], __fmul_rn(drift, dt));
+      xn[u] = reflect1(__fadd_rn(m, __fmul_rn(gz, z[u])));
+      xm[u] = reflect1(m);
+    }
+    *reinterpret_cast<float4*>(x_out + 4 * i) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    if (x_mean_out) *reinterpret_cast<float4*>(x_mean_out + 4 * i) = make_float4(xm[0], xm[1], xm[2], xm[3]);
+  }
+  size_t t = (n4 << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < n) {
+    const float drift = -__fmul_rn(g2, score[t]);
+    const float m = __fadd_rn(x[t], __fmul_rn(drift, dt));
+    x_out[t] = reflect1(__fadd_rn(m, __fmul_rn(gz, zt[t])));
+    if (x_mean_out) x_mean_out[t] = reflect1(m);
+  }
+}
+
+__global__ void step_advance_kernel(int32_t* ctr) { *ctr += 1; }
+
+static inline int stream_grid(size_t work_items, int threads, int max_waves = 8) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  size_t cap = static_cast<size_t>(kNumSMs) * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace rd
+
+using namespace rd;
+
+extern "C" {
+
+const char* rd_last_error(void) { return err_buf(); }
+int rd_version(void) { return 100; }
+int rd_device_cc(void) {
+  int dev = 0, maj = 0, min = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev);
+  if (e != cudaSuccess) return -fail(static_cast<int>(e), "rd_device_cc: %s", cudaGetErrorString(e));
+  return maj * 10 + min;
+}
+
+int rd_reflect_f32(const float* x, float* out, size_t n, void* stream) {
+  if (n == 0) return RD_OK;
+  RD_REQUIRE(x && out, "rd_reflect_f32: null pointer");
+  RD_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "rd_reflect_f32: pointers must be 16-byte aligned");
+  // 148 SMs x 8 resident CTAs of 256 threads, 4 x 128-bit loads in flight per thread
+  int grid = stream_grid((n + 3) / 4, 256, 8);
+  reflect_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, n);
+  return check_launch("reflect_kernel");
+}
+
+int rd_inside_f32(const float* x, uint8_t* ok, size_t B, size_t D, void* stream) {
+  if (B == 0) return RD_OK;
+  RD_REQUIRE(x && ok, "rd_inside_f32: null pointer");
+  size_t blocks = (B * 32 + 255) / 256;
+  inside_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ok, B, D);
+  return check_launch("inside_kernel");
+}
+
+int rd_score_hk_f32(const float* x, const float* x_orig, const float* sigma, float sigma_scalar, float* out,
+                    size_t B, size_t D, int efs, int refls, float min_cutoff, void* stream) {
+  if (B == 0 || D == 0) return RD_OK;
+  RD_REQUIRE(x && x_orig && out, "rd_score_hk_f32: null pointer");
+  RD_REQUIRE(efs >= 0 && efs <= HK_MAX_EFS, "rd_score_hk_f32: efs must be in [0,%d]", HK_MAX_EFS);
+  RD_REQUIRE(refls >= 0, "rd_score_hk_f32: refls must be >= 0");
+  RD_REQUIRE(D <= (1u << 20), "rd_score_hk_f32: D too large");
+  size_t blocks = (B + HK_SPB - 1) / HK_SPB;
+  bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_orig) |
+                               reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec)
+    score_hk_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
+                                                                       static_cast<int>(D), efs, refls, min_cutoff);
+  else
+    score_hk_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
+                                                                       static_cast<int>(D), efs, refls, min_cutoff);
+  return check_launch("score_hk_kernel");
+}
+
+int rd_philox_normal_f32(float* out, size_t n, uint64_t seed, uint32_t draw, void* stream) {
+  if (n == 0) return RD_OK;
+  RD_REQUIRE(out && (n % 4 == 0), "rd_philox_normal_f32: n must be a multiple of 4");
+  int grid = stream_grid(n / 4, 256, 8);
+  philox_normal_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n / 4, seed, draw);
+  return check_launch("philox_normal_kernel");
+}
+
+int rd_cfg_combine_f32(const float* s, const float* w, float w_scalar, float* out, size_t B, size_t D,
+                       void* stream) {
+  if (B * D == 0) return RD_OK;
+  RD_REQUIRE(s && out, "rd_cfg_combine_f32: null pointer");
+  int grid = stream_grid(B * D, 256, 8);
+  cfg_combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(s, w, w_scalar, out, B, D);
+  return check_launch("cfg_combine_kernel");
+}
+
+int rd_pc_norms(const float* grad, const float* noise, float* partial, int* nblk, size_t B, size_t D,
+                uint64_t seed, uint32_t draw_base, const int32_t* step_ctr, size_t noise_step_stride,
+                void* stream) {
+  RD_REQUIRE(grad && partial && B > 0 && D > 0, "rd_pc_norms: bad arguments");
+  RD_REQUIRE(noise || (D % 4 == 0), "rd_pc_norms: Philox noise needs D %% 4 == 0");
+  int blocks = static_cast<int>((B + PC_SPB - 1) / PC_SPB);
+  if (nblk) *nblk = blocks;
+  pc_norms_kernel<<<blocks, 32 * PC_SPB, 0, static_cast<cudaStream_t>(stream)>>>(
+      grad, noise, partial, B, static_cast<int>(D), seed, draw_base, step_ctr, noise_step_stride);
+  return check_launch("pc_norms_kernel");
+}
+
+int rd_pc_corrector_apply(const float* x, const float* grad, const float* noise, const float* partial,
+                          int nblk, float snr, float* x_out, float* x_mean_out, float* stats_out, size_t B,
+                          size_t D, uint64_t seed, uint32_t draw_base, const int32_t* step_ctr,
+                          size_t noise_step_stride, void* stream) {
+  RD_REQUIRE(x && grad && partial && x_out && B > 0 && D > 0 && nblk > 0, "rd_pc_corrector_apply: bad arguments");
+  const size_t n = B * D;
+  RD_REQUIRE(noise || (n % 4 == 0), "rd_pc_corrector_apply: Philox noise needs B*D %% 4 == 0");
+  int grid = stream_grid((n + 3) / 4, 256, 8);
+  pc_corrector_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, grad, noise, partial, nblk, snr, x_out, x_mean_out, stats_out, B, n, seed, draw_base, step_ctr,
+      noise_step_stride);
+  return check_launch("pc_corrector_apply_kernel");
+}
+
+int rd_pc_predictor_step(const float* x, const float* score, const float* z, const float* g_table, float dt,
+                         float sqrt_dt, float* x_out, float* x_mean_out, size_t B, size_t D, uint64_t seed,
+                         uint32_t draw_base, int32_t* step_ctr, size_t noise_step_stride, int advance_ctr,
+                         void* stream) {
+  RD_REQUIRE(x && score && g_table && x_out && B > 0 && D > 0, "rd_pc_predictor_step: bad arguments");
+  const size_t n = B * D;
+  RD_REQUIRE(z || (n % 4 == 0), "rd_pc_predictor_step: Philox noise needs B*D %% 4 == 0");
+  RD_REQUIRE(!advance_ctr || step_ctr, "rd_pc_predictor_step: advance_ctr needs step_ctr");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int grid = stream_grid((n + 3) / 4, 256, 8);
+  pc_predictor_kernel<<<grid, 256, 0, st>>>(x, score, z, g_table, dt, sqrt_dt, x_out, x_mean_out, n, seed,
+                                            draw_base, step_ctr, noise_step_stride);
+  int rc = check_launch("pc_predictor_kernel");
+  if (rc != RD_OK) return rc;
+  if (advance_ctr) {
+    step_advance_kernel<<<1, 1, 0, st>>>(step_ctr);
+    rc = check_launch("step_advance_kernel");
+  }
+  return rc;
+}
+
+}  // extern "C"
