@@ -75,11 +75,12 @@ int rd_pc_corrector_apply(const float* x, const float* grad, const float* noise,
                           size_t noise_step_stride, void* stream);
 /* x_mean = reflect(x + g^2*score/N) ; x_out = reflect(x_mean_raw + g*sqrt(1/N)*z).
  * g_table[step] = diffusion coefficient, dt = -1/N (negative), sqrt_dt = sqrt(1/N).
- * z == NULL -> Philox(seed, draw = draw_base + 2*step + 1).  advance_ctr != 0 -> (*step_ctr)++ after use. */
+ * z == NULL -> Philox(seed, draw = draw_base + 2*step + 1).  advance_ctr != 0 -> (*step_ctr)++ after use.
+ * g_per_sample != 0 -> g_table is [B], one coefficient per sample (the update_fn API with arbitrary t). */
 int rd_pc_predictor_step(const float* x, const float* score, const float* z, const float* g_table, float dt,
                          float sqrt_dt, float* x_out, float* x_mean_out, size_t B, size_t D, uint64_t seed,
                          uint32_t draw_base, int32_t* step_ctr, size_t noise_step_stride, int advance_ctr,
-                         void* stream);
+                         int g_per_sample, void* stream);
 /* out = (1+w)*s_cond - w*s_uncond ; s is [2B, D] (cond first); w: [B] device or NULL -> w_scalar. */
 int rd_cfg_combine_f32(const float* s, const float* w, float w_scalar, float* out, size_t B, size_t D,
                        void* stream);
@@ -98,7 +99,7 @@ enum rd_op_kind {
 
 typedef struct rd_conv_src {
   const void* ptr; /* bf16 NHWC [B2, Hs, Ws, C] */
-  int32_t C;       /* channels of this source (multiple of 64 after padding rules, see pack.py) */
+  int32_t C;       /* channels of this source (multiple of 8; the total over sources a multiple of 64) */
   int32_t Hs, Ws;  /* stored spatial size; gathered to (H_in, W_in) by nearest mapping */
 } rd_conv_src;
 
@@ -109,16 +110,14 @@ typedef struct rd_op_conv {
   int32_t pad;                /* 1: 3x3 pad 1 (output H_in x W_in); 0: pad (0,1,0,1)    */
   int32_t stride;             /* 1 or 2 (2 only with pad == 0: Downsample)              */
   int32_t H_out, W_out;
-  int32_t ntaps;              /* 9 (3x3) or 0 (no 3x3 part, 1x1 only)                   */
-  int32_t C_out;              /* N of the GEMM: 64,128,192,256                          */
+  int32_t ntaps;              /* 9 (3x3 conv) or 1 (1x1: NIN / attention projections)   */
+  int32_t C_out;              /* N of the GEMM: multiple of 32, <= 256                  */
   int32_t gn_groups;          /* 0: no GroupNorm/SiLU prologue                          */
   int32_t gn_silu;            /* 1: SiLU after GN (ResBlock), 0: GN only (attention)    */
   float gn_eps;
   const float* gn_gamma;      /* [C_in_total] */
   const float* gn_beta;
-  const void* w_taps;         /* bf16 packed [chunk][tap][8][C_out][8]  (GN'd operand)  */
-  const void* w_1x1;          /* bf16 packed [chunk][8][C_out][8] applied to RAW input (NIN shortcut) or NULL */
-  int32_t one_by_one_on_gn;   /* 1: the 1x1 weights act on the GN'd operand (attention q/k/v, NIN_3 has gn_groups=0) */
+  const void* w;              /* bf16 packed [C_in/64][ntaps][8][C_out][8] (rdb200/pack.py) */
   const float* bias;          /* [C_out] (sum of all fused biases) */
   const float* tproj;         /* [B2, tproj_stride] per-sample additive term or NULL */
   int32_t tproj_stride, tproj_off;
@@ -126,7 +125,7 @@ typedef struct rd_op_conv {
   float out_scale;            /* 1/sqrt(2) when skip_rescale, else 1 */
   void* out;                  /* bf16 NHWC [B2,H_out,W_out,C_out] */
   int32_t B2;                 /* samples (2B under CFG) */
-  int32_t samples_per_cta;    /* chosen by the host planner */
+  int32_t samples_per_cta;    /* 0: library picks the tile geometry; >0: planner override */
 } rd_op_conv;
 
 typedef struct rd_op_attn {
@@ -139,10 +138,11 @@ typedef struct rd_op_temb {
   const float* time_table; /* [n_steps, temb_dim] = time_mlp(fourier(log sigma_i)) + label_emb.bias */
   const float* label_w;    /* [temb_dim, num_classes] label_emb.weight */
   const float* labels;     /* [B2, num_classes] */
-  const void* dense_w;     /* bf16? no: fp32 [n_out_total, temb_dim] all Dense_0 weights stacked */
+  const void* dense_w;     /* fp32 [n_out_total, temb_dim]: all Dense_0 weights stacked */
   const float* dense_b;    /* [n_out_total] */
   float* out;              /* [B2, n_out_total] */
-  const int32_t* step_ctr; /* device step index (NULL -> row 0) */
+  const int32_t* step_ctr; /* device step index: every sample uses row *step_ctr (sampler) ... */
+  const int32_t* row_idx;  /* ... unless row_idx != NULL: per-sample table row [B2] (generic forward) */
   int32_t B2, temb_dim, num_classes, n_out_total;
 } rd_op_temb;
 

@@ -343,12 +343,14 @@ __global__ void __launch_bounds__(256) pc_predictor_kernel(const float* __restri
                                                            float dt, float sqrt_dt, float* __restrict__ x_out,
                                                            float* __restrict__ x_mean_out, size_t n, uint64_t seed,
                                                            uint32_t draw_base, const int32_t* __restrict__ step_ctr,
-                                                           size_t noise_step_stride) {
+                                                           size_t noise_step_stride, int g_per_sample, size_t D) {
   const int32_t step = step_ctr ? *step_ctr : 0;
   if (zt) zt += static_cast<size_t>(step) * noise_step_stride;
-  const float g = g_table[step];
-  const float g2 = __fmul_rn(g, g);
-  const float gz = __fmul_rn(g, sqrt_dt);
+  // g_per_sample: g_table holds one diffusion coefficient per sample (update_fn API with arbitrary t[B]);
+  // otherwise one per sampler step, shared by the batch
+  float g = g_per_sample ? 0.0f : g_table[step];
+  float g2 = __fmul_rn(g, g);
+  float gz = __fmul_rn(g, sqrt_dt);
   const uint32_t draw = draw_base + 2u * static_cast<uint32_t>(step) + 1u;
   const size_t n4 = n >> 2;
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -367,6 +369,11 @@ __global__ void __launch_bounds__(256) pc_predictor_kernel(const float* __restri
     float xm[4], xn[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      if (g_per_sample) {
+        g = g_table[(4 * i + u) / D];
+        g2 = __fmul_rn(g, g);
+        gz = __fmul_rn(g, sqrt_dt);
+      }
       const float drift = -__fmul_rn(g2, ss[u]);
       const float m = __fadd_rn(xs[u], __fmul_rn(drift, dt));
       xn[u] = reflect1(__fadd_rn(m, __fmul_rn(gz, z[u])));
@@ -377,6 +384,11 @@ __global__ void __launch_bounds__(256) pc_predictor_kernel(const float* __restri
   }
   size_t t = (n4 << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t < n) {
+    if (g_per_sample) {
+      g = g_table[t / D];
+      g2 = __fmul_rn(g, g);
+      gz = __fmul_rn(g, sqrt_dt);
+    }
     const float drift = -__fmul_rn(g2, score[t]);
     const float m = __fadd_rn(x[t], __fmul_rn(drift, dt));
     x_out[t] = reflect1(__fadd_rn(m, __fmul_rn(gz, zt[t])));
@@ -496,7 +508,7 @@ int rd_pc_corrector_apply(const float* x, const float* grad, const float* noise,
 int rd_pc_predictor_step(const float* x, const float* score, const float* z, const float* g_table, float dt,
                          float sqrt_dt, float* x_out, float* x_mean_out, size_t B, size_t D, uint64_t seed,
                          uint32_t draw_base, int32_t* step_ctr, size_t noise_step_stride, int advance_ctr,
-                         void* stream) {
+                         int g_per_sample, void* stream) {
   RD_REQUIRE(x && score && g_table && x_out && B > 0 && D > 0, "rd_pc_predictor_step: bad arguments");
   const size_t n = B * D;
   RD_REQUIRE(z || (n % 4 == 0), "rd_pc_predictor_step: Philox noise needs B*D %% 4 == 0");
@@ -504,7 +516,7 @@ int rd_pc_predictor_step(const float* x, const float* score, const float* z, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int grid = stream_grid((n + 3) / 4, 256, 8);
   pc_predictor_kernel<<<grid, 256, 0, st>>>(x, score, z, g_table, dt, sqrt_dt, x_out, x_mean_out, n, seed,
-                                            draw_base, step_ctr, noise_step_stride);
+                                            draw_base, step_ctr, noise_step_stride, g_per_sample, D);
   int rc = check_launch("pc_predictor_kernel");
   if (rc != RD_OK) return rc;
   if (advance_ctr) {
