@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- GTO-Halo samples/s of the 1000-step CFG reflected predictor-corrector sampler.
+
+Workload (BASELINE.json configs[2] = "C3" per GPU; N GPUs x 8192 = configs[3] "C4" at N=8):
+  NCSN++ 2D (8x9 latents, nf 64, ch_mult [1,2,2], 2 res blocks, attention at 8x9, conditional),
+  random-init weights, RVESDE(0.01, 5, N=1000), eps 1e-5, Langevin corrector (snr 0.01, 1 step) +
+  reflected Euler-Maruyama predictor, classifier-free guidance w=1.5, batch 8192 per GPU.
+
+A "step" is ONE predictor-corrector iteration over the batch (2 guided-score evaluations = 4
+network passes per sample + both fused updates) -- the unit the sampler repeats 999 times; all
+iterations launch the same captured graph, so
+    samples/s = n_gpus * B / (999 * ms_per_step + final all-gather).
+The default --steps 999 times exactly one full sampler pass.  `e2e` times one complete call of the
+public drop-in API (sampling.get_sampling_fn(...)(model, weight, class_labels)) with host labels,
+the CPU-drawn prior copied H2D (as the reference does) and the samples copied back to the host.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "optimized-diffusion-model_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+SDE_N = 1000
+ITERS_PER_PASS = SDE_N - 1          # sampling.py:330 skips the last grid point
+FLOP_PER_SAMPLE_FORWARD = 207.374848e6   # 8x9, attention at 8 (torch FlopCounter, 2*MAC)
+FLOP_PER_SAMPLE = FLOP_PER_SAMPLE_FORWARD * 2 * 2 * ITERS_PER_PASS  # CFG x2, corrector+predictor x2
+METRIC = "GTO-Halo samples/sec (1000-step CFG PC sampler)"
+UNIT = "samples/s"
+WORKLOAD = ("C3: GTO-Halo NCSN++ 2D (8x9, nf64, ch_mult [1,2,2], 2 res blocks, attn@8x9, CFG w=1.5) random-init, "
+            "reflected PC sampler (Langevin snr 0.01 + Euler-Maruyama), 1000 steps, batch 8192 per GPU")
+
+
+def model_config(corrector="langevin"):
+    m = types.SimpleNamespace(
+        name="ncsnpp", channels=1, image_size=8, image_width=9, num_classes=1, cond_drop_prob=0.5, conditional=True,
+        init_scale=0.0, ema_rate=0.999, nf=64, ch_mult=[1, 2, 2], num_res_blocks=2, attn_resolutions=[8],
+        resamp_with_conv=True, embedding_type="fourier", fourier_scale=16, skip_rescale=True, nonlinearity="swish",
+        fir=False, fir_kernel=[1, 3, 3, 1], dropout=0.2, scale_by_sigma=False)
+    s = types.SimpleNamespace(method="pc", predictor="euler_maruyama", corrector=corrector, denoiser="none", snr=0.01,
+                              n_steps_each=1)
+    return types.SimpleNamespace(model=m, sampling=s)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0)),
+                "bf16_burst": d.get("bf16_tflops", 1590.0), "hbm_gbs": d.get("hbm_gbs", 6650.0), "source": "measured"}
+    return {"bf16_tflops": 1400.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        busy = [v for v in sm if v > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_iteration_time(B, steps, warmup, threads):
+    """The reference's algorithm on the host cores: the oracle port (oracle/rd_oracle.py, bit-identical to
+    the reference on the golden fixtures) -- one PC iteration = 2 guided scores at 2B + both updates."""
+    from oracle import rd_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.NetConfig()
+    sd = O.synth_state_dict(cfg, seed=0, degenerate=True)  # magnitude pattern of the untouched reference init
+    sched = O.VESchedule(0.01, 5.0, SDE_N, 1.0, 1e-5)
+    scfg = O.SamplerConfig()
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand((B, 1, 8, 9), generator=g)
+    labels = torch.rand((B, 1), generator=g)
+    ts = sched.timesteps()
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            noise = torch.randn((2, B, 1, 8, 9), generator=g)
+            t0 = time.perf_counter()
+            vec_t = torch.ones(B) * ts[i]
+            sig = sched.sigma(vec_t)
+            grad = O.guided_score(x, sig, labels, 1.5, sd, cfg)
+            x, _, _ = O.corrector_step(x, grad, noise[0], scfg.snr)
+            score = O.guided_score(x, sig, labels, 1.5, sd, cfg)
+            x, _ = O.predictor_step(x, score, sched.diffusion(vec_t), SDE_N, noise[1])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = args.ref_batch
+    # bounded sample: keep the whole K-step run within ~2 minutes by shrinking the per-step batch if needed
+    probe = cpu_reference_iteration_time(B, 1, 1, threads)[0]
+    budget_s = 120.0
+    if probe * (args.steps + args.warmup) > budget_s:
+        B = max(8, int(B * budget_s / (probe * (args.steps + args.warmup))) // 8 * 8)
+    times = cpu_reference_iteration_time(B, args.steps, args.warmup, threads)
+    ms = 1e3 * sum(times) / len(times)
+    value = B / (ITERS_PER_PASS * ms / 1e3)
+    sample = (f"oracle port of the reference sampler (fp32 PyTorch CPU, TF32 n/a), batch {B}, {args.steps} PC iterations "
+              f"timed after {args.warmup} warm-up, extrapolated linearly to the 999 iterations of a full pass; "
+              f"loadavg {os.getloadavg()[0]:.1f}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "reference_batch": B,
+                                                           "step": "one PC iteration on the host CPU cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=ITERS_PER_PASS)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8192, help="samples per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=128)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    import cube
+    import sampling
+    import sde_lib
+    from models import utils as mutils
+    from rdb200 import dist as rdd
+
+    B = args.batch
+    cfg = model_config()
+    torch.manual_seed(0)
+    model = mutils.create_model(cfg).to(dev).eval()   # untouched reference init: timing is weight-independent
+    sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=SDE_N)
+    labels_host = torch.rand((B, 1), generator=torch.Generator().manual_seed(1 + rank)).pin_memory()
+    labels = labels_host.to(dev, non_blocking=True)
+    x0 = torch.rand((B, 1, 8, 9), generator=torch.Generator().manual_seed(2 + rank)).to(dev)
+    eng = model.rd_sampler_engine(B, 8, 9, dev, sde, 1e-5, 0.01, 1, cfg=True)
+    seed = rdd.philox_seed_for_rank(3, rank)
+
+    def run_iters(n, start=0):
+        return eng.sample(x0, labels, 1.5, seed=seed, use_graph=True, n_iter=n, start_step=start)
+
+    # ---- warm-up (also builds and instantiates the CUDA graph)
+    run_iters(args.warmup)
+    torch.cuda.synchronize(dev)
+    # ---- timed region: exactly K iterations, CUDA events on the engine's stream, barrier + sync on both sides
+    K = args.steps
+    clocks = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    done = 0
+    e0.record(torch.cuda.current_stream(dev))
+    while done < K:  # the step counter indexes the sigma grid, so long runs wrap in chunks of one full pass
+        n = min(K - done, ITERS_PER_PASS)
+        xs = run_iters(n)
+        done += n
+    e1.record(torch.cuda.current_stream(dev))
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop()
+    ms_total = e0.elapsed_time(e1)
+    inside = bool(cube.inside(xs).all())
+    # final all-gather (once per sampler pass)
+    ag_ms = 0.0
+    if world > 1:
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rdd.all_gather_batch(xs, B * world)
+        torch.cuda.synchronize(dev)
+        a0.record(); full = rdd.all_gather_batch(xs, B * world); a1.record()
+        torch.cuda.synchronize(dev)
+        ag_ms = a0.elapsed_time(a1)
+        assert full.shape[0] == B * world
+        t = torch.tensor([ms_total, ag_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ag_ms = float(t[0]), float(t[1])
+    ms_per_step = ms_total / K
+    pass_s = (ITERS_PER_PASS * ms_per_step + ag_ms) / 1e3
+    value = world * B / pass_s
+
+    # ---- roofline of the dominant kernel (tcgen05 conv/NIN implicit GEMM): per-op CUDA events, eager replay
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        eng.run_plan()
+        torch.cuda.synchronize(dev)
+        reps = 3
+        per_op = [0.0] * eng.n_ops
+        for _ in range(reps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(eng.n_ops + 1)]
+            ev[0].record()
+            for i in range(eng.n_ops):
+                eng.run_ops(i, 1)
+                ev[i + 1].record()
+            torch.cuda.synchronize(dev)
+            for i in range(eng.n_ops):
+                per_op[i] += ev[i].elapsed_time(ev[i + 1]) / reps
+        conv_ms = sum(t for t, n in zip(per_op, eng.op_names) if eng.op_kinds[n] == "conv")
+        fwd_ms = sum(per_op)
+        conv_flop = eng.conv_flops_per_sample * eng.B2
+        achieved = conv_flop / (conv_ms / 1e3) / 1e12
+        n_conv = sum(1 for n in eng.op_names if eng.op_kinds[n] == "conv")
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (all %d launches of one guided-score evaluation)" % n_conv,
+                "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
+                "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                "avg_launch_ms": conv_ms / n_conv, "share_of_forward": conv_ms / fwd_ms,
+                "algorithmic_flop_per_launch_avg": conv_flop / n_conv,
+                "sampler_frac": value / world * FLOP_PER_SAMPLE / (pk["bf16_tflops"] * 1e12)}
+
+    # ---- e2e through the public drop-in API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        fn = sampling.get_sampling_fn(cfg, sde, (B, 1, 8, 9), 1e-5, dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        lab = labels_host.to(dev, non_blocking=True)                  # H2D from pinned memory
+        samples, nfe = fn(model, weight=1.5, class_labels=lab, rd_seed=seed)   # prior drawn on the CPU and copied H2D inside
+        if world > 1:
+            samples = rdd.all_gather_batch(samples, B * world)
+        host = samples.cpu()                                           # D2H of the result
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        assert bool(((host >= 0) & (host <= 1)).all())
+        e2e = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(B * 4 + B * 72 * 4),
+               "d2h_bytes_per_step": int(host.numel() * 4 // (world if world > 1 else 1)), "seconds_per_pass": dt,
+               "call": "sampling.get_sampling_fn(config, sde, shape, eps, device)(model, weight=1.5, class_labels=...)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        times = cpu_reference_iteration_time(args.ref_batch, 2, 1, threads)
+        ms = 1e3 * sum(times) / len(times)
+        cpu = {"value": args.ref_batch / (ITERS_PER_PASS * ms / 1e3), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"oracle port, batch {args.ref_batch}, 2 PC iterations after 1 warm-up ({ms:.0f} ms each), "
+                         f"extrapolated to 999 iterations; loadavg {os.getloadavg()[0]:.1f}"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                       "step": "one PC iteration (2 CFG score evaluations + fused corrector and predictor updates); "
+                               "value = global_batch / (999*ms_per_step + all-gather)",
+                       "l2": "activations of one iteration (>5 GB at 2B=16384) exceed the 126 MB L2; no flush needed",
+                       "noise": "in-kernel Philox", "cuda_graph": True, "all_gather_ms": ag_ms,
+                       "all_samples_inside_cube": inside, "parallelism": f"batch-sharded x{world}, no collective in the loop"},
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": eng.launches_per_iter() * K}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,8 @@ class Engine:
         check(lib().rd_plan_create(C.byref(self.plan)), "rd_plan_create")
         self._temb_op_index = 0
         self.op_names: List[str] = []
+        self.op_kinds: Dict[str, str] = {}
+        self.conv_flops_per_sample = 0.0  # algorithmic 2*M*N*K of the tcgen05 launches, valid pixels only
         self.tensors: Dict[str, _Act] = {}
         self._sampler = None
         self._built_for_table = None
@@ -132,6 +134,8 @@ class Engine:
     def _add(self, op: D.Op, name: str):
         check(lib().rd_plan_add(self.plan, C.byref(op)), f"rd_plan_add({name})")
         self.op_names.append(name)
+        self.op_kinds[name] = {D.RD_OP_CONV: "conv", D.RD_OP_ATTN_CORE: "attn", D.RD_OP_TEMB: "temb",
+                               D.RD_OP_IN_CONV: "in_conv", D.RD_OP_OUT_HEAD: "out_head"}[op.kind]
 
     def _conv(self, name, srcs, H_in, W_in, C_out, wname, bias, *, ntaps=9, pad=1, stride=1, gn=None, silu=1,
               tproj_off=None, residual=None, out_scale=1.0) -> _Act:
@@ -158,6 +162,7 @@ class Engine:
         if residual is not None:
             c.residual = residual.ptr
         c.out_scale, c.out, c.B2, c.samples_per_cta = out_scale, out.ptr, self.B2, 0
+        self.conv_flops_per_sample += 2.0 * Ho * Wo * C_out * sum(s.C for s in srcs) * ntaps
         self._add(op, name)
         self.tensors[name] = out
         return out
@@ -339,6 +344,7 @@ class SamplerEngine(Engine):
         self.partial = torch.zeros((2 * ((B + 7) // 8) + 8,), dtype=torch.float32, device=self.device)
         self._tape = None
         self._desc = None
+        self.stream = torch.cuda.Stream(device=self.device)
 
     def refresh_tables(self):
         """Re-tabulate the batch-invariant time embedding after a weight change."""
@@ -362,8 +368,9 @@ class SamplerEngine(Engine):
 
     @torch.no_grad()
     def sample(self, x0: torch.Tensor, labels: Optional[torch.Tensor], weight, *, tape: Optional[torch.Tensor] = None,
-               seed: int = 0, use_graph: bool = True, n_iter: Optional[int] = None) -> torch.Tensor:
-        """Run iterations 0..N-2 (the last grid point is skipped, sampling.py:330) and return x."""
+               seed: int = 0, use_graph: bool = True, n_iter: Optional[int] = None, start_step: int = 0) -> torch.Tensor:
+        """Run iterations start_step..N-2 (the last grid point is skipped, sampling.py:330) and return x.
+        `start_step` / `n_iter` restrict the range (teacher-forced single-step parity checks)."""
         sp = self.spec
         self.x.copy_(x0.reshape(self.x.shape))
         if sp.conditional and self.cfg:
@@ -376,15 +383,20 @@ class SamplerEngine(Engine):
                 self.cfg_w.fill_(float(weight))
             else:
                 self.cfg_w.copy_(weight.reshape(-1))
-        self.step_ctr.zero_()
+        self.step_ctr.fill_(start_step)
         if tape is not None:
             tape = tape.to(self.device, torch.float32).contiguous()
-        if self._sampler is None or (tape is not None) or (self._tape is not None) or self._desc.seed != seed:
-            self._make_sampler(tape, seed)
-            self.run_plan()  # one eager pass: first-use kernel attribute calls must not happen under capture
-        iters = (self.N - 1) if n_iter is None else n_iter
-        check(lib().rd_sampler_run(self._sampler, iters, 1 if use_graph else 0, stream_ptr(self.device)),
-              "rd_sampler_run")
+        iters = (self.N - 1 - start_step) if n_iter is None else n_iter
+        # stream capture is not allowed on the legacy default stream: the loop runs on the engine's own stream
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            if self._sampler is None or (tape is not None) or (self._tape is not None) or self._desc.seed != seed:
+                self._make_sampler(tape, seed)
+                self.run_plan()  # one eager pass: first-use kernel attribute calls must not happen under capture
+            check(lib().rd_sampler_run(self._sampler, iters, 1 if use_graph else 0, stream_ptr(self.device)),
+                  "rd_sampler_run")
+        cur.wait_stream(self.stream)
         return self.x.clone()
 
     def launches_per_iter(self) -> int:

@@ -1,0 +1,117 @@
+"""CPU: host-side logic of the drop-in -- registries, SDE tables, weight packing layouts, plan
+topology bookkeeping, error behaviour without a GPU, and the 2-rank batch sharding (gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cube
+import sampling
+import sde_lib
+from models import utils as mutils
+from oracle import rd_oracle as O
+from rdb200 import pack
+from rdb200.engine import NetSpec, spec_from_config
+from helpers import load_golden, make_config, oracle_cfg, same_bits
+
+
+def test_registries_and_errors():
+    assert sampling.get_predictor("euler_maruyama") is sampling.ReflectedEulerMaruyamaPredictor
+    assert sampling.get_corrector("langevin") is sampling.ReflectedLangevinCorrector
+    assert sampling.get_corrector("none") is sampling.NoneCorrector
+    assert set(("network", "mean", "none")) <= set(sampling._DENOISERS)
+    with pytest.raises(ValueError):
+        sampling.register_predictor(name="euler_maruyama")(type("X", (), {}))
+    with pytest.raises(KeyError):
+        sampling.get_predictor("nope")
+    cfg = make_config()
+    cfg.sampling.method = "bogus"
+    with pytest.raises(ValueError):
+        sampling.get_sampling_fn(cfg, sde_lib.RVESDE(0.01, 5, 10), (2, 1, 8, 9), 1e-5, "cpu")
+    with pytest.raises(ValueError):
+        mutils.register_model(name="ncsnpp")(type("Y", (), {}))
+    assert mutils.get_model("ncsnpp").__name__ == "NCSNpp"
+
+
+def test_sde_tables_match_reference_schedule():
+    g = load_golden("schedule.npz")
+    sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=1000)
+    t, sigma, gg = sde.step_tables(1e-5)
+    assert same_bits(t, torch.from_numpy(g["t"])) and same_bits(sigma, torch.from_numpy(g["sigma"]))
+    assert same_bits(gg, torch.from_numpy(g["g"]))
+    # API surface of the reverse SDE
+    r = sde.reverse(lambda x, tt: torch.ones_like(x), probability_flow=False)
+    x = torch.zeros(3, 1, 2, 2)
+    drift, diff = r.sde(x, torch.tensor([1.0, 0.5, 0.1]))
+    assert drift.shape == x.shape and torch.allclose(drift[:, 0, 0, 0], -(diff ** 2))
+    assert r.N == 1000 and r.T == 1
+    f, G = sde.discretize(x, torch.tensor([1.0, 0.5, 0.0]))
+    assert float(G[2]) == pytest.approx(float(sde.discrete_sigmas[0]))
+    assert sde.prior_sampling((2, 3)).shape == (2, 3) and float(sde.prior_logp(x).abs().sum()) == 0
+
+
+def test_no_cpu_fallback():
+    x = torch.rand(4, 1, 8, 9)
+    for fn in (cube.reflect, cube.inside, lambda t: cube.score_hk(t, t, 0.1)):
+        with pytest.raises(RuntimeError):
+            fn(x)
+    model = mutils.create_model(make_config())
+    with pytest.raises(RuntimeError):
+        model(x, torch.ones(4), class_labels=torch.zeros(4, 1))
+
+
+def test_module_matches_reference_state_dict_spec():
+    model = mutils.create_model(make_config())
+    sd = model.state_dict()
+    shapes = O.state_dict_shapes(oracle_cfg())
+    assert set(sd) == set(shapes) and all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    assert sum(p.numel() for p in model.parameters() if p.requires_grad) == 6254913 - 64  # time_embed.W is frozen
+    spec = spec_from_config(make_config())
+    assert len(spec.res_blocks()) == 17 and spec.attn_blocks() == ["down_attn.0", "down_attn.1", "up_attn.6", "up_attn.7", "up_attn.8"]
+    # degenerate init pattern of the reference
+    assert float(sd["down_blocks.0.Conv_1.weight"].std()) < 1e-5 < float(sd["down_blocks.0.Conv_0.weight"].std())
+    assert float(sd["out_conv.weight"].std()) < 1e-5 and float(sd["out_conv.bias"].abs().sum()) == 0
+    # 9x9 shipped shape gates attention on image_size only
+    assert spec_from_config(make_config(9, 9)).attn_blocks() == spec.attn_blocks()
+
+
+def test_weight_packing_layout():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(128, 192, 3, 3, generator=g)
+    p = pack.pack_conv3x3(w)
+    assert p.shape == (3, 9, 8, 128, 8) and p.dtype == torch.bfloat16
+    for (n, c, dy, dx) in [(0, 0, 0, 0), (5, 70, 1, 2), (127, 191, 2, 2), (64, 64, 0, 1)]:
+        assert float(p[c // 64, dy * 3 + dx, (c % 64) // 8, n, c % 8]) == float(w[n, c, dy, dx].to(torch.bfloat16))
+    W = torch.randn(256, 128, generator=g)
+    q = pack.pack_1x1(W)
+    assert q.shape == (4, 1, 8, 128, 8)
+    for (k, n) in [(0, 0), (100, 17), (255, 127)]:
+        assert float(q[k // 64, 0, (k % 64) // 8, n, k % 8]) == float(W[k, n].to(torch.bfloat16))
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from rdb200 import dist as rdd
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = rdd.shard_range(10, rank, world)
+    local = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1, 1).repeat(1, 1, 2, 2)
+    full = rdd.all_gather_batch(local, 10)
+    q.put((rank, lo, hi, full[:, 0, 0, 0].tolist(), rdd.philox_seed_for_rank(123, rank)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_batch_sharding_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert (res[0][1], res[0][2], res[1][1], res[1][2]) == (0, 5, 5, 10)
+    assert res[0][3] == list(map(float, range(10))) == res[1][3]
+    assert res[0][4] != res[1][4]

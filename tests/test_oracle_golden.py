@@ -1,0 +1,105 @@
+"""CPU: the oracle restatement (oracle/rd_oracle.py) against the golden vectors produced by the
+unmodified reference (oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rd_oracle as O
+from helpers import load_golden, oracle_cfg, rel_to_max, same_bits
+
+
+def test_reflect_bitwise():
+    g = load_golden("reflect.npz")
+    assert same_bits(O.reflect(torch.from_numpy(g["x"])), torch.from_numpy(g["y"]))
+
+
+def test_reflect_properties():
+    x = (torch.rand(100000, generator=torch.Generator().manual_seed(1)) - 0.5) * 40
+    r = O.reflect(x)
+    assert bool(((r >= 0) & (r <= 1)).all())
+    assert same_bits(O.reflect(r), r)  # idempotent, bitwise
+    # even and 2-periodic only up to an ulp of the intermediate
+    assert float((O.reflect(-x) - r).abs().max()) <= 1e-6
+    assert float((O.reflect(x + 2) - r).abs().max()) <= 4e-6
+
+
+def test_score_hk_against_reference():
+    g = load_golden("score_hk.npz")
+    for i in range(g["x"].shape[0]):
+        x, x0, sg = (torch.from_numpy(g[k][i]) for k in ("x", "x_orig", "sigma"))
+        r = O.score_hk(x, x0, sg)
+        ref32, ref64 = torch.from_numpy(g["ref32"][i]), torch.from_numpy(g["ref64"][i])
+        scale = float(ref64.abs().max())
+        floor = float((ref32.double() - ref64).abs().max())
+        assert float((r - ref32).abs().max()) <= 2e-6 * scale + 2 * floor + 1e-30
+
+
+def test_score_hk_float_sigma():
+    g = load_golden("score_hk.npz")
+    x, x0 = torch.from_numpy(g["x"][-1]), torch.from_numpy(g["x_orig"][-1])
+    ref = torch.from_numpy(g["ref32_sigma_float_025"])
+    assert rel_to_max(O.score_hk(x, x0, 0.25), ref) <= 1e-5
+
+
+def test_schedule_bitwise():
+    g = load_golden("schedule.npz")
+    s = O.VESchedule(0.01, 5.0, 1000, 1.0, 1e-5)
+    t = s.timesteps()
+    assert same_bits(t, torch.from_numpy(g["t"]))
+    assert same_bits(s.sigma(t), torch.from_numpy(g["sigma"]))
+    assert same_bits(s.diffusion(t), torch.from_numpy(g["g"]))
+
+
+def test_pc_single_steps_bitwise():
+    g = load_golden("pc_steps.npz")
+    sch = load_golden("schedule.npz")
+    x, score, z = (torch.from_numpy(g[k]) for k in ("x", "score", "z"))
+    B = x.shape[0]
+    for idx in (0, 300, 700, 998):
+        gi = torch.full((B,), float(sch["g"][idx]))
+        xp, xpm = O.predictor_step(x, score, gi, 1000, z)
+        xc, xcm, _ = O.corrector_step(x, score, z, 0.01)
+        assert same_bits(xp, torch.from_numpy(g[f"pred_x_{idx}"])) and same_bits(xpm, torch.from_numpy(g[f"pred_mean_{idx}"]))
+        assert same_bits(xc, torch.from_numpy(g[f"corr_x_{idx}"])) and same_bits(xcm, torch.from_numpy(g[f"corr_mean_{idx}"]))
+
+
+@pytest.mark.parametrize("tag,isz", [("8x9", 8), ("9x9", 9)])
+def test_forward_against_reference(tag, isz):
+    g = load_golden(f"forward_{tag}.npz")
+    cfg = oracle_cfg(isz, isz)
+    sd = O.synth_state_dict(cfg, seed=7)
+    x, sigma, labels = (torch.from_numpy(g[k]) for k in ("x", "sigma", "labels"))
+    taps = {}
+    with torch.no_grad():
+        y = O.ncsnpp_forward(x, sigma, labels, sd, cfg, taps=taps)
+        s = O.guided_score(x, O.VESchedule().sigma(torch.from_numpy(g["t_cfg"])), labels, torch.from_numpy(g["w_cfg"]), sd, cfg)
+    assert rel_to_max(y, torch.from_numpy(g["y"])) <= 2e-5
+    assert rel_to_max(s, torch.from_numpy(g["score_cfg"])) <= 2e-5
+    for k in g.files:
+        if k.startswith("tap:"):
+            assert rel_to_max(taps[k[4:]], torch.from_numpy(g[k])) <= 2e-5, k
+
+
+def test_state_dict_spec_counts():
+    shapes = O.state_dict_shapes(oracle_cfg(8, 8))
+    assert len(shapes) == 261
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 6254913
+    no_attn = O.state_dict_shapes(O.NetConfig(image_size=8, attn_resolutions=()))
+    assert sum(int(np.prod(s)) for s in no_attn.values()) == 6171073
+
+
+@pytest.mark.parametrize("tag,corrector", [("pc_N30", "langevin"), ("pred_only_N30", "none")])
+def test_sampler_tape_replay(tag, corrector):
+    g = load_golden(f"sampler_{tag}.npz")
+    N, B = int(g["N"]), int(g["B"])
+    cfg = oracle_cfg(8, 8)
+    sd = O.synth_state_dict(cfg, seed=7)
+    n_draws = (N - 1) * (2 if corrector == "langevin" else 1)
+    x0, noise = O.make_tape(B, (1, 8, 9), n_draws, seed=int(g["tape_seed"]))
+    labels, w = torch.from_numpy(g["labels"]), float(g["w"])
+    with torch.no_grad():
+        x = O.pc_sampler(lambda xx, sg: O.guided_score(xx, sg, labels, w, sd, cfg),
+                         O.VESchedule(0.01, 5.0, N, 1.0, 1e-5), O.SamplerConfig(corrector=corrector), x0, noise)
+    assert bool(O.inside(x).all())
+    assert float((x - torch.from_numpy(g["x_final"])).abs().max()) <= 5e-4
+    assert int(g["nfe"]) == N * 2  # the reference reports N*(n_steps+1) regardless of the corrector
