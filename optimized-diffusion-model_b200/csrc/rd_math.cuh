@@ -11,13 +11,15 @@ namespace rd {
 // cube.reflect (reference cube.py:47-49):  m = x % 2 (torch floor-mod) ; m > 1 -> 2 - m.
 // torch.remainder(x, 2) == fmod(x,2) (+2 when negative and non-zero).  x - 2*floor(x/2) evaluated
 // with a single rounding (fma) is the same real number rounded once, hence bit-identical, except
-// for two corner cases handled explicitly: x == +-0 (fmod keeps the sign of zero) and negative
+// for corner cases handled explicitly: x == +-0 and exact multiples of 2 (fmod keeps the sign of the
+// dividend on a zero result: reflect(-2) = -0.0) and negative
 // denormals whose half rounds to -0 (floor must still be -1).  NaN/Inf -> NaN like torch.
 __device__ __forceinline__ float reflect1(float x) {
   if (x == 0.0f) return x;
   float k = floorf(x * 0.5f);
   if (x < 0.0f && k == 0.0f) k = -1.0f;
   float m = __fmaf_rn(-2.0f, k, x);
+  if (m == 0.0f) m = copysignf(0.0f, x);  // fmod keeps the dividend's sign on exact multiples of 2
   return (m > 1.0f) ? (2.0f - m) : m;
 }
 
