@@ -1,8 +1,8 @@
 #!/bin/bash
 # one GPU session: parity tests, smoke, bench, launch list, one full ncu capture of the conv kernel
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-tail -25 gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q -s ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+grep -E 'passed|failed|FAILED|Error|forward|sampler ' gpurun_out/pytest_gpu.log | tail -30
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 timeout 600 python bench.py --steps ${BENCH_STEPS:-60} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
