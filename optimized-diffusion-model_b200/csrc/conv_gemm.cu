@@ -35,6 +35,7 @@ constexpr int EPI_WARPS = 4;        // warps 4..7
 constexpr int MAX_A_STAGES = 3;
 constexpr int MAX_W_STAGES = 4;
 constexpr int MAX_HW = 32;  // gather maps
+constexpr int RC_MAX = 16;                           // pixels a transform thread may cache in registers
 constexpr int STAT_PAIRS = 256;                      // (sample, 8-channel chunk) pairs per statistics batch
 constexpr int STAT_SCRATCH_BYTES = XFORM_THREADS * 64;  // one 16-float partial record per transform thread
 
@@ -56,6 +57,7 @@ struct ConvParams {
   int a_stages, a_stage_bytes;
   int w_resident, w_stages, w_slab_bytes, n_slabs;
   int acc_bufs;
+  int xmode, rc_PS;  // transform mode: 1 = register-cached single pass (rc_PS pixel slices), 0 = streaming
   int tmem_cols;     // power of two >= acc_bufs*n_tiles*N
   int groups, cpg, silu;
   float eps;
@@ -82,7 +84,7 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(const ConvParams& p) 
   L.a_off = 0;
   L.w_off = p.a_stages * p.a_stage_bytes;
   L.tab_off = L.w_off + (p.w_resident ? p.n_slabs : p.w_stages) * p.w_slab_bytes;
-  int tab = p.groups > 0 ? p.Cin * 12 + p.S * p.groups * 8 + STAT_SCRATCH_BYTES : 0;
+  int tab = (p.groups > 0 ? p.Cin * 12 + p.S * p.groups * 8 + STAT_SCRATCH_BYTES : 0) + p.S * p.H * p.W * 12 + 64;
   L.total = L.tab_off + (tab + 127) / 128 * 128;
   return L;
 }
@@ -124,11 +126,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   const ConvSmemLayout L = conv_smem_layout(p);
   unsigned char* As = smem + L.a_off;
   unsigned char* Ws = smem + L.w_off;
-  float* s_gamma = reinterpret_cast<float*>(smem + L.tab_off);
-  float* s_beta = s_gamma + p.Cin;
-  int* s_gidx = reinterpret_cast<int*>(s_beta + p.Cin);
-  float* s_stat = reinterpret_cast<float*>(s_gidx + p.Cin);  // [S][G][2]: (mean, rstd)
-  float* s_scr = s_stat + p.S * p.groups * 2;                // statistics scratch, STAT_SCRATCH_BYTES
+  // tables: source offsets [2][S*P] (int), staged rows [S*P] (u16), then the GroupNorm tables when used
+  int* t_off = reinterpret_cast<int*>(smem + L.tab_off);
+  unsigned short* t_row = reinterpret_cast<unsigned short*>(t_off + 2 * p.S * p.H * p.W);
+  const int gn_cin = p.groups > 0 ? p.Cin : 0;
+  float* s_gamma = reinterpret_cast<float*>(smem + L.tab_off + ((p.S * p.H * p.W * 10 + 63) / 64) * 64);
+  float* s_beta = s_gamma + gn_cin;
+  int* s_gidx = reinterpret_cast<int*>(s_beta + gn_cin);
+  float* s_stat = reinterpret_cast<float*>(s_gidx + gn_cin);  // [S][G][2]: (mean, rstd)
+  float* s_scr = s_stat + p.S * p.groups * 2;                 // statistics scratch, STAT_SCRATCH_BYTES (16-B aligned)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = p.H * p.W;
@@ -298,6 +304,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       const uint4 zero = make_uint4(0, 0, 0, 0);
       for (int i = xt; i < n16; i += XFORM_THREADS) a4[i] = zero;
     }
+    // group-invariant addressing tables: staged row and source element offset of every (sample, pixel)
+    for (int sp = xt; sp < p.S * P; sp += XFORM_THREADS) {
+      const int s = sp / P, px = sp - s * P;
+      const int y = px / p.W, x = px - y * p.W;
+      t_row[sp] = static_cast<unsigned short>(s * p.rps + (y + p.pad) * p.Wp + (x + p.pad));
+      t_off[sp] = ((s * p.Hs[0] + p.ymap[0][y]) * p.Ws[0] + p.xmap[0][x]) * p.C[0];
+      if (p.nsrc > 1) t_off[p.S * P + sp] = ((s * p.Hs[1] + p.ymap[1][y]) * p.Ws[1] + p.xmap[1][x]) * p.C[1];
+    }
     if (p.groups > 0) {
       for (int c = xt; c < p.Cin; c += XFORM_THREADS) {
         s_gamma[c] = p.gamma[c];
@@ -306,133 +320,213 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
     xform_bar();
+    const size_t gstride0 = static_cast<size_t>(p.S) * p.Hs[0] * p.Ws[0] * p.C[0];
+    const size_t gstride1 = static_cast<size_t>(p.S) * p.Hs[1] * p.Ws[1] * p.C[1];
+    const float inv_n = p.groups > 0 ? 1.0f / static_cast<float>(p.cpg * P) : 0.0f;
     int a_it = 0;
-    for (int li = 0; li < my_groups; ++li) {
-      const int g = blockIdx.x + li * gridDim.x;
-      const int sample0 = g * p.S;
-      const int S_act = min(p.S, p.B2 - sample0);
-      if (p.groups > 0) {
-        // ---- GroupNorm statistics of this group's samples (fp32), one pass over the bf16 input.
-        // Deterministic: per-thread partial sums go to a scratch table and are reduced in a fixed order
-        // (no atomics), in batches of samples so the scratch stays small.
-        const int spb = max(1, STAT_PAIRS / p.KC);
-        const float inv_n = 1.0f / static_cast<float>(p.cpg * P);
-        for (int sb = 0; sb < S_act; sb += spb) {
-          const int ns = min(spb, S_act - sb);
-          const int pairs = ns * p.KC;
-          int PS = XFORM_THREADS / pairs;
-          PS = max(1, min(PS, P));
-          for (int item = xt; item < pairs * PS; item += XFORM_THREADS) {
-            const int pair = item % pairs, slice = item / pairs;
-            const int s = pair / p.KC, kc = pair - s * p.KC;
-            float sum[8], sq[8];
+
+    // normalise + activate the 8 channels starting at c0 of sample s (of the group) in place
+    auto gn_apply = [&](uint4& raw, int s, int c0) {
+      float f[8];
+      unpack8(raw, f);
+      const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + c0), g1 = *reinterpret_cast<const float4*>(s_gamma + c0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(s_beta + c0), b1 = *reinterpret_cast<const float4*>(s_beta + c0 + 4);
+      const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float* st = s_stat + s * p.groups * 2;
+      if ((p.cpg & 7) == 0) {  // one group per 8-channel item
+        const float2 mr = *reinterpret_cast<const float2*>(st + 2 * (c0 / p.cpg));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; sq[j] = 0.0f; }
-            for (int px = slice; px < P; px += 4 * PS) {
-              uint4 raw[4];
+        for (int j = 0; j < 8; ++j) {
+          const float a = gam[j] * mr.y;
+          f[j] = fmaf(f[j], a, fmaf(-mr.x, a, bet[j]));
+        }
+      } else if (p.cpg == 4) {  // two groups per item
+        const float4 mr = *reinterpret_cast<const float4*>(st + 2 * (c0 >> 2));
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (px + u * PS < P) raw[u] = *item_ptr(p, sample0 + sb + s, px + u * PS, kc);
+        for (int j = 0; j < 8; ++j) {
+          const float a = gam[j] * (j < 4 ? mr.y : mr.w);
+          f[j] = fmaf(f[j], a, fmaf(-(j < 4 ? mr.x : mr.z), a, bet[j]));
+        }
+      } else {
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (px + u * PS < P) {
-                  float f[8];
-                  unpack8(raw[u], f);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
-                }
-            }
-            float4* dst = reinterpret_cast<float4*>(s_scr + (static_cast<size_t>(slice) * pairs + pair) * 16);
-            dst[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
-            dst[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
-            dst[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
-            dst[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
-          }
-          xform_bar();
-          for (int sg = xt; sg < ns * p.groups; sg += XFORM_THREADS) {
-            const int s = sg / p.groups, g = sg - s * p.groups;
-            float sum = 0.0f, sq = 0.0f;
-            for (int c = g * p.cpg; c < (g + 1) * p.cpg; ++c) {
-              const int pair = s * p.KC + (c >> 3), j = c & 7;
-              for (int slice = 0; slice < PS; ++slice) {
-                const float* src = s_scr + (static_cast<size_t>(slice) * pairs + pair) * 16;
-                sum += src[j];
-                sq += src[8 + j];
-              }
-            }
-            const float mean = sum * inv_n;
-            const float var = fmaxf(sq * inv_n - mean * mean, 0.0f);
-            s_stat[2 * ((sb + s) * p.groups + g)] = mean;
-            s_stat[2 * ((sb + s) * p.groups + g) + 1] = 1.0f / sqrtf(var + p.eps);
-          }
-          xform_bar();
+        for (int j = 0; j < 8; ++j) {
+          const float2 mr = *reinterpret_cast<const float2*>(st + 2 * s_gidx[c0 + j]);
+          const float a = gam[j] * mr.y;
+          f[j] = fmaf(f[j], a, fmaf(-mr.x, a, bet[j]));
         }
       }
-      // ---- stage the normalised / activated operand, one 64-channel chunk per ring stage
-      const int items = S_act * P * 8;
-      for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
-        const int stage = a_it % p.a_stages;
-        if (a_it >= p.a_stages) mbar_wait(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
-        uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes);
-        for (int base = xt; base < items; base += 4 * XFORM_THREADS) {
-          uint4 raw[4];
-          int kcl[4], row[4], sidx[4];
+      if (p.silu) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int item = base + u * XFORM_THREADS;
-            if (item < items) {
-              kcl[u] = item & 7;
-              const int sp = item >> 3;
-              const int s = sp / P, px = sp - s * P;
-              const int y = px / p.W, x = px - y * p.W;
-              sidx[u] = s;
-              row[u] = s * p.rps + (y + p.pad) * p.Wp + (x + p.pad);
-              raw[u] = *item_ptr(p, sample0 + s, px, chunk * 8 + kcl[u]);
-            }
-          }
+        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+      }
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int item = base + u * XFORM_THREADS;
-            if (item < items) {
-              if (p.groups > 0) {
-                float f[8];
-                unpack8(raw[u], f);
-                const int c0 = (chunk * 8 + kcl[u]) * 8;
-                const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + c0), g1 = *reinterpret_cast<const float4*>(s_gamma + c0 + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(s_beta + c0), b1 = *reinterpret_cast<const float4*>(s_beta + c0 + 4);
-                const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                const float* st = s_stat + sidx[u] * p.groups * 2;
-                if ((p.cpg & 7) == 0) {  // one group per 8-channel item
-                  const float2 mr = *reinterpret_cast<const float2*>(st + 2 * (c0 / p.cpg));
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float a = gam[j] * mr.y;
-                    f[j] = fmaf(f[j], a, fmaf(-mr.x, a, bet[j]));
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float2 mr = *reinterpret_cast<const float2*>(st + 2 * s_gidx[c0 + j]);
-                    const float a = gam[j] * mr.y;
-                    f[j] = fmaf(f[j], a, fmaf(-mr.x, a, bet[j]));
-                  }
-                }
-                if (p.silu) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
-                }
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw[u]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              }
-              a4[kcl[u] * p.R + row[u]] = raw[u];
-            }
+      for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    };
+    // fixed-order reduction of the per-thread partial records into per-(sample, group) mean / rstd
+    auto stat_reduce = [&](int s_first, int ns, int pairs, int PS) {
+      for (int sg = xt; sg < ns * p.groups; sg += XFORM_THREADS) {
+        const int s = sg / p.groups, g = sg - s * p.groups;
+        float sum = 0.0f, sq = 0.0f;
+        for (int c = g * p.cpg; c < (g + 1) * p.cpg; ++c) {
+          const int pair = s * p.KC + (c >> 3), j = c & 7;
+          for (int slice = 0; slice < PS; ++slice) {
+            const float* src = s_scr + (static_cast<size_t>(slice) * pairs + pair) * 16;
+            sum += src[j];
+            sq += src[8 + j];
           }
         }
-        fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
+        const float mean = sum * inv_n;
+        const float var = fmaxf(sq * inv_n - mean * mean, 0.0f);
+        s_stat[2 * ((s_first + s) * p.groups + g)] = mean;
+        s_stat[2 * ((s_first + s) * p.groups + g) + 1] = 1.0f / sqrtf(var + p.eps);
+      }
+    };
+
+    if (p.xmode == 1) {
+      // ---------------- register-cached mode: every thread owns one (sample, 8-channel chunk, pixel slice);
+      // its pixels are read from global memory ONCE, kept in registers across the statistics barrier,
+      // then normalised and written to the operand ring.
+      const int pairs = p.S * p.KC, PS = p.rc_PS;
+      const int pair = xt % pairs, slice = xt / pairs;
+      const int s = pair / p.KC, kc = pair - s * p.KC;
+      const bool owner = xt < pairs * PS;
+      const int which = (kc * 8 < p.C[0]) ? 0 : 1;
+      const int coff = kc * 8 - (which ? p.C[0] : 0);
+      const int* toff = t_off + (which ? p.S * P : 0) + s * P;
+      const unsigned short* trow = t_row + s * P;
+      const int my_chunk = kc >> 3, kcl = kc & 7;
+      for (int li = 0; li < my_groups; ++li) {
+        const int g = blockIdx.x + li * gridDim.x;
+        const int S_act = min(p.S, p.B2 - g * p.S);
+        const bool active = owner && s < S_act;
+        const __nv_bfloat16* gbase = p.src[which] + static_cast<size_t>(g) * (which ? gstride1 : gstride0) + coff;
+        uint4 raw[RC_MAX];
+#pragma unroll
+        for (int k = 0; k < RC_MAX; ++k) {
+          const int px = slice + k * PS;
+          if (active && px < P) raw[k] = *reinterpret_cast<const uint4*>(gbase + toff[px]);
+        }
+        float sum[8], sq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; sq[j] = 0.0f; }
+#pragma unroll
+        for (int k = 0; k < RC_MAX; ++k) {
+          if (active && slice + k * PS < P) {
+            float f[8];
+            unpack8(raw[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
+          }
+        }
+        if (owner) {
+          float4* dst = reinterpret_cast<float4*>(s_scr + (static_cast<size_t>(slice) * pairs + pair) * 16);
+          dst[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
+          dst[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
+          dst[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+          dst[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
+        }
         xform_bar();
-        if (xt == 0) mbar_arrive(&bar_a_full[stage]);
+        stat_reduce(0, S_act, pairs, PS);
+        xform_bar();
+        for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
+          const int stage = a_it % p.a_stages;
+          if (a_it >= p.a_stages) mbar_wait(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
+          if (active && chunk == my_chunk) {
+            uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes) + kcl * p.R;
+#pragma unroll
+            for (int k = 0; k < RC_MAX; ++k) {
+              const int px = slice + k * PS;
+              if (px < P) {
+                gn_apply(raw[k], s, kc * 8);
+                a4[trow[px]] = raw[k];
+              }
+            }
+          }
+          fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
+          xform_bar();
+          if (xt == 0) mbar_arrive(&bar_a_full[stage]);
+        }
+      }
+    } else {
+      // ---------------- streaming mode: optional statistics pass, then a copy/normalise pass per chunk
+      for (int li = 0; li < my_groups; ++li) {
+        const int g = blockIdx.x + li * gridDim.x;
+        const int S_act = min(p.S, p.B2 - g * p.S);
+        const __nv_bfloat16* gb0 = p.src[0] + static_cast<size_t>(g) * gstride0;
+        const __nv_bfloat16* gb1 = p.nsrc > 1 ? p.src[1] + static_cast<size_t>(g) * gstride1 : gb0;
+        if (p.groups > 0) {
+          // deterministic statistics: per-thread partial records reduced in a fixed order, in batches of samples
+          const int spb = max(1, STAT_PAIRS / p.KC);
+          for (int sb = 0; sb < S_act; sb += spb) {
+            const int ns = min(spb, S_act - sb);
+            const int pairs = ns * p.KC;
+            int PS = XFORM_THREADS / pairs;
+            PS = max(1, min(PS, P));
+            for (int item = xt; item < pairs * PS; item += XFORM_THREADS) {
+              const int pair = item % pairs, slice = item / pairs;
+              const int s = pair / p.KC, kc = pair - s * p.KC;
+              const int which = (kc * 8 < p.C[0]) ? 0 : 1;
+              const __nv_bfloat16* base = (which ? gb1 - p.C[0] : gb0) + kc * 8;
+              const int* toff = t_off + (which ? p.S * P : 0) + (sb + s) * P;
+              float sum[8], sq[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; sq[j] = 0.0f; }
+              for (int px = slice; px < P; px += 4 * PS) {
+                uint4 raw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (px + u * PS < P) raw[u] = *reinterpret_cast<const uint4*>(base + toff[px + u * PS]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (px + u * PS < P) {
+                    float f[8];
+                    unpack8(raw[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
+                  }
+              }
+              float4* dst = reinterpret_cast<float4*>(s_scr + (static_cast<size_t>(slice) * pairs + pair) * 16);
+              dst[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
+              dst[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
+              dst[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+              dst[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
+            }
+            xform_bar();
+            stat_reduce(sb, ns, pairs, PS);
+            xform_bar();
+          }
+        }
+        const int items = S_act * P * 8;
+        for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
+          const int stage = a_it % p.a_stages;
+          if (a_it >= p.a_stages) mbar_wait(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
+          uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes);
+          const int which = (chunk * 64 < p.C[0]) ? 0 : 1;  // C[0] is a multiple of 64 whenever there are two sources
+          const __nv_bfloat16* base = (which ? gb1 - p.C[0] : gb0) + chunk * 64;
+          const int* toff = t_off + (which ? p.S * P : 0);
+          for (int b0 = xt; b0 < items; b0 += 8 * XFORM_THREADS) {
+            uint4 raw[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int item = b0 + u * XFORM_THREADS;
+              if (item < items) raw[u] = *reinterpret_cast<const uint4*>(base + toff[item >> 3] + (item & 7) * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int item = b0 + u * XFORM_THREADS;
+              if (item < items) {
+                const int sp = item >> 3, kcl = item & 7;
+                if (p.groups > 0) gn_apply(raw[u], sp / P, chunk * 64 + kcl * 8);
+                a4[kcl * p.R + t_row[sp]] = raw[u];
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          xform_bar();
+          if (xt == 0) mbar_arrive(&bar_a_full[stage]);
+        }
       }
     }
   }
@@ -488,6 +582,7 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     cin += op.src[i].C;
   }
   if (op.nsrc == 1) { p.C[1] = 0; }
+  else RD_REQUIRE(op.src[0].C % 64 == 0, "conv: with two sources the first must have a multiple of 64 channels");
   RD_REQUIRE(cin % 64 == 0, "conv: total input channels (%d) must be a multiple of 64", cin);
   p.nsrc = op.nsrc;
   p.H = op.H_in; p.W = op.W_in;
@@ -541,6 +636,13 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
       while (c.w_stages > 2 && conv_smem_layout(c).total > smem_cap) --c.w_stages;
       if (conv_smem_layout(c).total > smem_cap && c.a_stages == 3) c.a_stages = 2;
       if (conv_smem_layout(c).total > smem_cap) continue;
+    }
+    // transform mode: register-cached when every (sample, chunk) pair gets a thread and <= RC_MAX pixels
+    c.xmode = 0; c.rc_PS = 1;
+    if (p.groups > 0 && c.S * p.KC <= XFORM_THREADS) {
+      int ps = XFORM_THREADS / (c.S * p.KC);
+      if (ps > p.H * p.W) ps = p.H * p.W;
+      if ((p.H * p.W + ps - 1) / ps <= RC_MAX) { c.xmode = 1; c.rc_PS = ps; }
     }
     double score = static_cast<double>(c.S * valid_px) / (nt * 128);
     if (c.acc_bufs == 1) score *= 0.75;
