@@ -23,6 +23,7 @@
 //     samples, so the A operand of tap (dy,dx) is the same buffer with the UMMA descriptor start
 //     address advanced by (dy*Wp+dx)*16 B: nine taps, no im2col, no data movement (validated on B200 by
 //     tools/probe_umma.cu).  Outputs at padding rows are computed and dropped.
+//   * All index arithmetic is group-invariant and tabulated once per CTA in shared memory.
 #include <cstring>
 #include "rd_common.h"
 #include "rd_ptx.cuh"
@@ -34,10 +35,15 @@ constexpr int XFORM_THREADS = 320;  // warps 2,3,8..15
 constexpr int EPI_WARPS = 4;        // warps 4..7
 constexpr int MAX_A_STAGES = 3;
 constexpr int MAX_W_STAGES = 4;
-constexpr int MAX_HW = 32;  // gather maps
-constexpr int RC_MAX = 16;                           // pixels a transform thread may cache in registers
-constexpr int STAT_PAIRS = 256;                      // (sample, 8-channel chunk) pairs per statistics batch
+constexpr int MAX_HW = 32;                              // gather maps
+constexpr int STAT_PAIRS = 256;                         // (sample, 8-channel chunk) pairs per statistics batch (streaming mode)
 constexpr int STAT_SCRATCH_BYTES = XFORM_THREADS * 64;  // one 16-float partial record per transform thread
+
+// GroupNorm flavour of the operand transform (template parameter GNM)
+constexpr int GNM_NONE = 0;     // plain copy (NIN shortcut, up/down-sampling convs, attention output projection)
+constexpr int GNM_CPG8 = 1;     // channels-per-group multiple of 8: one group per 8-channel item
+constexpr int GNM_CPG4 = 2;     // 4 channels per group: two groups per item
+constexpr int GNM_GENERAL = 3;  // anything else (192 channels / 32 groups = 6)
 
 struct ConvParams {
   const __nv_bfloat16* src[2];
@@ -57,7 +63,8 @@ struct ConvParams {
   int a_stages, a_stage_bytes;
   int w_resident, w_stages, w_slab_bytes, n_slabs;
   int acc_bufs;
-  int xmode, rc_PS;  // transform mode: 1 = register-cached single pass (rc_PS pixel slices), 0 = streaming
+  int xmode, rc_PS;  // transform mode: >0 = register-cached single pass (value = register slots, rc_PS pixel slices), 0 = streaming
+  int gnm;
   int tmem_cols;     // power of two >= acc_bufs*n_tiles*N
   int groups, cpg, silu;
   float eps;
@@ -74,48 +81,54 @@ struct ConvParams {
   unsigned char ymap[2][MAX_HW], xmap[2][MAX_HW];
 };
 
-// dynamic shared memory carve-up (bytes)
+// dynamic shared memory carve-up (bytes, every region 128-B aligned)
 struct ConvSmemLayout {
-  int a_off, w_off, tab_off, total;
+  int a_off, w_off, toff_off, trow_off, torow_off, tos_off, bt_off, gn_off, total;
 };
+
+__host__ __device__ inline int align128(int v) { return (v + 127) / 128 * 128; }
 
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(const ConvParams& p) {
   ConvSmemLayout L;
+  const int SP = p.S * p.H * p.W, rows = p.n_tiles * 128;
   L.a_off = 0;
   L.w_off = p.a_stages * p.a_stage_bytes;
-  L.tab_off = L.w_off + (p.w_resident ? p.n_slabs : p.w_stages) * p.w_slab_bytes;
-  int tab = (p.groups > 0 ? p.Cin * 12 + p.S * p.groups * 8 + STAT_SCRATCH_BYTES : 0) + p.S * p.H * p.W * 12 + 64;
-  L.total = L.tab_off + (tab + 127) / 128 * 128;
+  L.toff_off = L.w_off + (p.w_resident ? p.n_slabs : p.w_stages) * p.w_slab_bytes;
+  L.trow_off = L.toff_off + align128(2 * SP * 4);  // source element offsets [2][S*P]
+  L.torow_off = L.trow_off + align128(SP * 2);     // staged row of every (sample, pixel)
+  L.tos_off = L.torow_off + align128(rows * 4);    // output element offset of every accumulator row (-1: dropped)
+  L.bt_off = L.tos_off + align128(rows);           // sample index of every accumulator row
+  L.gn_off = L.bt_off + align128(2 * p.S * p.N * 4);  // (bias + temb projection) * out_scale, double-buffered
+  const int gn = p.groups > 0 ? p.Cin * 12 + p.S * p.groups * 8 + STAT_SCRATCH_BYTES : 0;
+  L.total = L.gn_off + align128(gn);
   return L;
-}
-
-__device__ __forceinline__ const __nv_bfloat16* src_pixel(const ConvParams& p, int which, int sample, int y, int x) {
-  const int sy = p.ymap[which][y], sx = p.xmap[which][x];
-  return p.src[which] + ((static_cast<size_t>(sample) * p.Hs[which] + sy) * p.Ws[which] + sx) * p.C[which];
 }
 
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 __device__ __forceinline__ void xform_bar() { asm volatile("bar.sync 1, %0;" ::"n"(XFORM_THREADS) : "memory"); }
-
-// address of the 8-channel item (sample s of the group, pixel px, global k-chunk kc)
-__device__ __forceinline__ const uint4* item_ptr(const ConvParams& p, int sample, int px, int kc) {
-  const int y = px / p.W, x = px - y * p.W;
-  const int which = (kc * 8 < p.C[0]) ? 0 : 1;
-  const int coff = kc * 8 - (which ? p.C[0] : 0);
-  return reinterpret_cast<const uint4*>(src_pixel(p, which, sample, y, x) + coff);
-}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 __device__ __forceinline__ void unpack8(const uint4& raw, float (&f)[8]) {
-  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float2 v = __bfloat1622float2(h2[j]);
-    f[2 * j] = v.x;
-    f[2 * j + 1] = v.y;
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
   }
 }
 
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int GNM, int RC>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar_a_full[MAX_A_STAGES], bar_a_empty[MAX_A_STAGES];
@@ -126,15 +139,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   const ConvSmemLayout L = conv_smem_layout(p);
   unsigned char* As = smem + L.a_off;
   unsigned char* Ws = smem + L.w_off;
-  // tables: source offsets [2][S*P] (int), staged rows [S*P] (u16), then the GroupNorm tables when used
-  int* t_off = reinterpret_cast<int*>(smem + L.tab_off);
-  unsigned short* t_row = reinterpret_cast<unsigned short*>(t_off + 2 * p.S * p.H * p.W);
-  const int gn_cin = p.groups > 0 ? p.Cin : 0;
-  float* s_gamma = reinterpret_cast<float*>(smem + L.tab_off + ((p.S * p.H * p.W * 10 + 63) / 64) * 64);
-  float* s_beta = s_gamma + gn_cin;
-  int* s_gidx = reinterpret_cast<int*>(s_beta + gn_cin);
-  float* s_stat = reinterpret_cast<float*>(s_gidx + gn_cin);  // [S][G][2]: (mean, rstd)
-  float* s_scr = s_stat + p.S * p.groups * 2;                 // statistics scratch, STAT_SCRATCH_BYTES (16-B aligned)
+  int* t_off = reinterpret_cast<int*>(smem + L.toff_off);
+  unsigned short* t_row = reinterpret_cast<unsigned short*>(smem + L.trow_off);
+  int* t_orow = reinterpret_cast<int*>(smem + L.torow_off);
+  unsigned char* t_os = smem + L.tos_off;
+  float* s_bt = reinterpret_cast<float*>(smem + L.bt_off);
+  float* s_gamma = reinterpret_cast<float*>(smem + L.gn_off);
+  float* s_beta = s_gamma + p.Cin;
+  int* s_gidx = reinterpret_cast<int*>(s_beta + p.Cin);
+  float* s_stat = reinterpret_cast<float*>(s_gidx + p.Cin);  // [S][G][2]: (mean, rstd)
+  float* s_scr = s_stat + p.S * p.groups * 2;                // statistics scratch (16-B aligned: S*G is even)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = p.H * p.W;
@@ -150,6 +164,27 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
+  // group-invariant index tables (all threads help)
+  for (int sp = tid; sp < p.S * P; sp += CONV_THREADS) {
+    const int s = sp / P, px = sp - s * P;
+    const int y = px / p.W, x = px - y * p.W;
+    t_row[sp] = static_cast<unsigned short>(s * p.rps + (y + p.pad) * p.Wp + (x + p.pad));
+    t_off[sp] = ((s * p.Hs[0] + p.ymap[0][y]) * p.Ws[0] + p.xmap[0][x]) * p.C[0];
+    if (p.nsrc > 1) t_off[p.S * P + sp] = ((s * p.Hs[1] + p.ymap[1][y]) * p.Ws[1] + p.xmap[1][x]) * p.C[1];
+  }
+  for (int row = tid; row < p.n_tiles * 128; row += CONV_THREADS) {
+    const int s = row / p.rps, rem = row - s * p.rps;
+    const int Y = rem / p.Wp, X = rem - Y * p.Wp;
+    bool valid = s < p.S;
+    int oy = Y, ox = X;
+    if (p.stride == 2) {
+      valid = valid && ((Y & 1) == 0) && ((X & 1) == 0);
+      oy = Y >> 1; ox = X >> 1;
+    }
+    valid = valid && oy < p.Ho && ox < p.Wo;
+    t_orow[row] = valid ? ((s * p.Ho + oy) * p.Wo + ox) * p.N : -1;
+    t_os[row] = static_cast<unsigned char>(valid ? s : 0);
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -158,8 +193,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   if (warp == 0) {
     // ================================================================ MMA issuer
     if (elect_one()) {
+      // Descriptors are built once; per MMA only the 14-bit start-address field (units of 16 B == staged
+      // rows) is advanced, so the issue loop is a couple of integer adds per tcgen05.mma.
       const uint32_t idesc = umma_idesc_bf16(128, p.N);
-      const uint32_t a_base = smem_u32(As), w_base = smem_u32(Ws);
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
+      const uint32_t a_lo0 = (smem_u32(As) >> 4) | (static_cast<uint32_t>(p.R) << 16);  // LBO = R*16 B
+      const uint32_t w_lo0 = (smem_u32(Ws) >> 4) | (static_cast<uint32_t>(p.N) << 16);  // LBO = N*16 B
+      const uint32_t a_stage_u = p.a_stage_bytes >> 4, w_slab_u = p.w_slab_bytes >> 4;
+      const uint32_t kstep_a = 2 * p.R, kstep_w = 2 * p.N;
       int a_it = 0, w_it = 0;
       if (p.w_resident && my_groups > 0) { mbar_wait(&bar_w_full[0], 0); tc_fence_after_sync(); }
       for (int li = 0; li < my_groups; ++li) {
@@ -170,28 +211,35 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           const int stage = a_it % p.a_stages;
           mbar_wait(&bar_a_full[stage], (a_it / p.a_stages) & 1);
           tc_fence_after_sync();
-          const uint32_t a_stage = a_base + stage * p.a_stage_bytes;
+          const uint32_t a_lo_stage = a_lo0 + stage * a_stage_u;
+          int shift = 0, col = 0;
           for (int tap = 0; tap < p.ntaps; ++tap) {
-            uint32_t wslab;
+            uint32_t w_lo;
             int ws = 0;
             if (p.w_resident) {
-              wslab = w_base + (chunk * p.ntaps + tap) * p.w_slab_bytes;
+              w_lo = w_lo0 + (chunk * p.ntaps + tap) * w_slab_u;
             } else {
               ws = w_it % p.w_stages;
               mbar_wait(&bar_w_full[ws], (w_it / p.w_stages) & 1);
               tc_fence_after_sync();
-              wslab = w_base + ws * p.w_slab_bytes;
+              w_lo = w_lo0 + ws * w_slab_u;
             }
-            const int shift = (p.ntaps == 9) ? (tap / 3) * p.Wp + (tap % 3) : 0;
+            uint32_t a_lo = a_lo_stage + shift;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t db = umma_desc_kmajor(wslab + (kk * 2 * p.N) * 16, p.N * 16, 128);
+              const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | w_lo;
+              uint32_t a_t = a_lo, d_t = acc;
               for (int tile = 0; tile < p.n_tiles; ++tile) {
-                const uint32_t a_addr = a_stage + ((kk * 2) * p.R + tile * 128 + shift) * 16;
-                umma_bf16_ss(acc + tile * p.N, umma_desc_kmajor(a_addr, p.R * 16, 128), db, idesc, (chunk | tap | kk) != 0);
+                umma_bf16_ss(d_t, (static_cast<uint64_t>(desc_hi) << 32) | a_t, db, idesc, (chunk | tap | kk) != 0);
+                a_t += 128;
+                d_t += p.N;
               }
+              a_lo += kstep_a;
+              w_lo += kstep_w;
             }
             if (!p.w_resident) { umma_commit(&bar_w_empty[ws]); ++w_it; }
+            // next tap: (dy,dx) -> row shift dy*Wp + dx
+            if (++col == 3) { col = 0; shift += p.Wp - 2; } else { shift += 1; }
           }
           umma_commit(&bar_a_empty[stage]);  // operand stage reusable once these MMAs have read it
         }
@@ -222,74 +270,80 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   } else if (warp >= 4 && warp < 8) {
     // ================================================================ epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int et = q * 32 + lane;
     const int cblocks = p.N / 32;
     const int nblocks = p.n_tiles * cblocks;
+    const size_t out_gstride = static_cast<size_t>(p.S) * p.Ho * p.Wo * p.N;
     for (int li = 0; li < my_groups; ++li) {
       const int g = blockIdx.x + li * gridDim.x;
       const int sample0 = g * p.S;
       const int S_act = min(p.S, p.B2 - sample0);
       const int buf = li % p.acc_bufs;
+      // per-(sample, channel) additive term (bias + Dense_0(SiLU(temb))) * out_scale, staged while the MMAs run
+      float* bt = s_bt + (li & 1) * p.S * p.N;
+      for (int i = et; i < S_act * p.N; i += EPI_WARPS * 32) {
+        const int s = i / p.N, c = i - s * p.N;
+        float v = __ldg(p.bias + c);
+        if (p.tproj) v += __ldg(p.tproj + static_cast<size_t>(sample0 + s) * p.tproj_stride + p.tproj_off + c);
+        bt[i] = v * p.out_scale;
+      }
+      epi_bar();
       mbar_wait(&bar_acc_full[buf], (li / p.acc_bufs) & 1);
       tc_fence_after_sync();
       const uint32_t acc = tmem + buf * p.n_tiles * p.N + (static_cast<uint32_t>(q * 32) << 16);
-      for (int tile = 0; tile < p.n_tiles; ++tile) {
-        const int row = tile * 128 + q * 32 + lane;
-        const int s = row / p.rps, rem = row - s * p.rps;
-        const int Y = rem / p.Wp, X = rem - Y * p.Wp;
-        bool valid = (s < S_act);
-        int oy = Y, ox = X;
-        if (p.stride == 2) {
-          valid = valid && ((Y & 1) == 0) && ((X & 1) == 0);
-          oy = Y >> 1; ox = X >> 1;
-        }
-        valid = valid && (oy < p.Ho) && (ox < p.Wo);
-        const int sample = sample0 + s;
-        const size_t o = valid ? ((static_cast<size_t>(sample) * p.Ho + oy) * p.Wo + ox) * p.N : 0;
-        const float* tp = (p.tproj && valid) ? p.tproj + static_cast<size_t>(sample) * p.tproj_stride + p.tproj_off : nullptr;
-        for (int cb = 0; cb < cblocks; ++cb) {
-          const int c0 = cb * 32;
-          uint32_t v[32];
-          tmem_ld32(acc + tile * p.N + c0, v);
-          // issue the global reads of this block's epilogue operands while the TMEM load is in flight
-          uint4 res[4];
-          float4 tv[8];
-          if (valid) {
-            if (p.residual) {
+      __nv_bfloat16* og = p.out + static_cast<size_t>(g) * out_gstride;
+      const __nv_bfloat16* rg = p.residual ? p.residual + static_cast<size_t>(g) * out_gstride : nullptr;
+      const int valid_limit = S_act * p.Ho * p.Wo * p.N;
+      uint4 res[4];
+      {  // residual prefetch for block 0
+        const int orow = t_orow[q * 32 + lane];
+        if (rg && orow >= 0 && orow < valid_limit) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(p.residual + o + c0 + 8 * j);
-            }
-            if (tp) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) tv[j] = __ldg(reinterpret_cast<const float4*>(tp + c0) + j);
-            }
-          }
-          tmem_ld_wait();
-          if (valid) {
-            uint32_t packed[16];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + j4);
-              float a[4] = {__uint_as_float(v[4 * j4]) + bv.x, __uint_as_float(v[4 * j4 + 1]) + bv.y,
-                            __uint_as_float(v[4 * j4 + 2]) + bv.z, __uint_as_float(v[4 * j4 + 3]) + bv.w};
-              if (tp) { a[0] += tv[j4].x; a[1] += tv[j4].y; a[2] += tv[j4].z; a[3] += tv[j4].w; }
-              if (p.residual) {
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(&res[j4 >> 1]) + 2 * (j4 & 1);
-                const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rw));
-                const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rw + 1));
-                a[0] += r0.x; a[1] += r0.y; a[2] += r1.x; a[3] += r1.y;
-              }
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(a[0] * p.out_scale, a[1] * p.out_scale);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(a[2] * p.out_scale, a[3] * p.out_scale);
-              packed[2 * j4] = *reinterpret_cast<uint32_t*>(&h0);
-              packed[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(p.out + o + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          }
+          for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rg + orow + 8 * j);
         }
       }
-      (void)nblocks;
+      for (int blk = 0; blk < nblocks; ++blk) {
+        const int tile = blk / cblocks, c0 = (blk - tile * cblocks) * 32;
+        const int row = tile * 128 + q * 32 + lane;
+        const int orow = t_orow[row];
+        const bool valid = orow >= 0 && orow < valid_limit;
+        uint32_t v[32];
+        tmem_ld32(acc + tile * p.N + c0, v);
+        uint4 cur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = res[j];
+        if (rg && blk + 1 < nblocks) {  // prefetch the next block's residual while this one is processed
+          const int nt = (blk + 1) / cblocks, nc0 = (blk + 1 - nt * cblocks) * 32;
+          const int nor = t_orow[nt * 128 + q * 32 + lane];
+          if (nor >= 0 && nor < valid_limit) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rg + nor + nc0 + 8 * j);
+          }
+        }
+        tmem_ld_wait();
+        if (valid) {
+          const float* btr = bt + t_os[row] * p.N + c0;
+          uint4 outv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b0 = *reinterpret_cast<const float4*>(btr + 8 * j), b1 = *reinterpret_cast<const float4*>(btr + 8 * j + 4);
+            float a[8] = {fmaf(__uint_as_float(v[8 * j]), p.out_scale, b0.x), fmaf(__uint_as_float(v[8 * j + 1]), p.out_scale, b0.y),
+                          fmaf(__uint_as_float(v[8 * j + 2]), p.out_scale, b0.z), fmaf(__uint_as_float(v[8 * j + 3]), p.out_scale, b0.w),
+                          fmaf(__uint_as_float(v[8 * j + 4]), p.out_scale, b1.x), fmaf(__uint_as_float(v[8 * j + 5]), p.out_scale, b1.y),
+                          fmaf(__uint_as_float(v[8 * j + 6]), p.out_scale, b1.z), fmaf(__uint_as_float(v[8 * j + 7]), p.out_scale, b1.w)};
+            if (rg) {
+              float r[8];
+              unpack8(cur[j], r);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = fmaf(r[e], p.out_scale, a[e]);
+            }
+            outv[j] = pack8(a);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(og + orow + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = outv[j];
+        }
+      }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
@@ -304,15 +358,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       const uint4 zero = make_uint4(0, 0, 0, 0);
       for (int i = xt; i < n16; i += XFORM_THREADS) a4[i] = zero;
     }
-    // group-invariant addressing tables: staged row and source element offset of every (sample, pixel)
-    for (int sp = xt; sp < p.S * P; sp += XFORM_THREADS) {
-      const int s = sp / P, px = sp - s * P;
-      const int y = px / p.W, x = px - y * p.W;
-      t_row[sp] = static_cast<unsigned short>(s * p.rps + (y + p.pad) * p.Wp + (x + p.pad));
-      t_off[sp] = ((s * p.Hs[0] + p.ymap[0][y]) * p.Ws[0] + p.xmap[0][x]) * p.C[0];
-      if (p.nsrc > 1) t_off[p.S * P + sp] = ((s * p.Hs[1] + p.ymap[1][y]) * p.Ws[1] + p.xmap[1][x]) * p.C[1];
-    }
-    if (p.groups > 0) {
+    if (GNM != GNM_NONE) {
       for (int c = xt; c < p.Cin; c += XFORM_THREADS) {
         s_gamma[c] = p.gamma[c];
         s_beta[c] = p.beta[c];
@@ -322,60 +368,66 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     xform_bar();
     const size_t gstride0 = static_cast<size_t>(p.S) * p.Hs[0] * p.Ws[0] * p.C[0];
     const size_t gstride1 = static_cast<size_t>(p.S) * p.Hs[1] * p.Ws[1] * p.C[1];
-    const float inv_n = p.groups > 0 ? 1.0f / static_cast<float>(p.cpg * P) : 0.0f;
+    const float inv_n = GNM != GNM_NONE ? 1.0f / static_cast<float>(p.cpg * P) : 0.0f;
     int a_it = 0;
 
-    // normalise + activate the 8 channels starting at c0 of sample s (of the group) in place
-    auto gn_apply = [&](uint4& raw, int s, int c0) {
-      float f[8];
-      unpack8(raw, f);
+    // per-channel affine (a, b) with y = x*a + b for the 8 channels starting at c0 of sample s
+    auto gn_coeffs = [&](int s, int c0, float (&ca)[8], float (&cb)[8]) {
       const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + c0), g1 = *reinterpret_cast<const float4*>(s_gamma + c0 + 4);
       const float4 b0 = *reinterpret_cast<const float4*>(s_beta + c0), b1 = *reinterpret_cast<const float4*>(s_beta + c0 + 4);
       const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       const float* st = s_stat + s * p.groups * 2;
-      if ((p.cpg & 7) == 0) {  // one group per 8-channel item
+      if (GNM == GNM_CPG8) {
         const float2 mr = *reinterpret_cast<const float2*>(st + 2 * (c0 / p.cpg));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = gam[j] * mr.y;
-          f[j] = fmaf(f[j], a, fmaf(-mr.x, a, bet[j]));
-        }
-      } else if (p.cpg == 4) {  // two groups per item
+        for (int j = 0; j < 8; ++j) { ca[j] = gam[j] * mr.y; cb[j] = fmaf(-mr.x, ca[j], bet[j]); }
+      } else if (GNM == GNM_CPG4) {
         const float4 mr = *reinterpret_cast<const float4*>(st + 2 * (c0 >> 2));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float a = gam[j] * (j < 4 ? mr.y : mr.w);
-          f[j] = fmaf(f[j], a, fmaf(-(j < 4 ? mr.x : mr.z), a, bet[j]));
+          ca[j] = gam[j] * (j < 4 ? mr.y : mr.w);
+          cb[j] = fmaf(-(j < 4 ? mr.x : mr.z), ca[j], bet[j]);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 mr = *reinterpret_cast<const float2*>(st + 2 * s_gidx[c0 + j]);
-          const float a = gam[j] * mr.y;
-          f[j] = fmaf(f[j], a, fmaf(-mr.x, a, bet[j]));
+          ca[j] = gam[j] * mr.y;
+          cb[j] = fmaf(-mr.x, ca[j], bet[j]);
         }
       }
+    };
+    auto gn_apply = [&](uint4& raw, const float (&ca)[8], const float (&cb)[8]) {
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], ca[j], cb[j]);
       if (p.silu) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
       }
-      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      raw = pack8(f);
     };
-    // fixed-order reduction of the per-thread partial records into per-(sample, group) mean / rstd
+    // fixed-order two-step reduction of the per-thread partial records into per-(sample, group) mean / rstd:
+    // (1) every (pair, value) column is summed over the pixel slices by its own thread, (2) one thread per
+    // (sample, group) adds its cpg channels.  Contains one transform barrier.
     auto stat_reduce = [&](int s_first, int ns, int pairs, int PS) {
+      if (PS > 1) {
+        for (int col = xt; col < pairs * 16; col += XFORM_THREADS) {
+          float acc = s_scr[col];
+          for (int slice = 1; slice < PS; ++slice) acc += s_scr[static_cast<size_t>(slice) * pairs * 16 + col];
+          s_scr[col] = acc;
+        }
+        xform_bar();
+      }
       for (int sg = xt; sg < ns * p.groups; sg += XFORM_THREADS) {
         const int s = sg / p.groups, g = sg - s * p.groups;
         float sum = 0.0f, sq = 0.0f;
         for (int c = g * p.cpg; c < (g + 1) * p.cpg; ++c) {
-          const int pair = s * p.KC + (c >> 3), j = c & 7;
-          for (int slice = 0; slice < PS; ++slice) {
-            const float* src = s_scr + (static_cast<size_t>(slice) * pairs + pair) * 16;
-            sum += src[j];
-            sq += src[8 + j];
-          }
+          const float* src = s_scr + static_cast<size_t>(s * p.KC + (c >> 3)) * 16 + (c & 7);
+          sum += src[0];
+          sq += src[8];
         }
         const float mean = sum * inv_n;
         const float var = fmaxf(sq * inv_n - mean * mean, 0.0f);
@@ -383,11 +435,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         s_stat[2 * ((s_first + s) * p.groups + g) + 1] = 1.0f / sqrtf(var + p.eps);
       }
     };
+    auto put_record = [&](int idx, const float (&sum)[8], const float (&sq)[8]) {
+      float4* dst = reinterpret_cast<float4*>(s_scr + static_cast<size_t>(idx) * 16);
+      dst[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
+      dst[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
+      dst[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+      dst[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
+    };
 
-    if (p.xmode == 1) {
+    if (RC > 0) {
       // ---------------- register-cached mode: every thread owns one (sample, 8-channel chunk, pixel slice);
       // its pixels are read from global memory ONCE, kept in registers across the statistics barrier,
-      // then normalised and written to the operand ring.
+      // then normalised and written to the operand ring.  With RC == 8 the next group's pixels are
+      // already in flight while the current group is being normalised.
       const int pairs = p.S * p.KC, PS = p.rc_PS;
       const int pair = xt % pairs, slice = xt / pairs;
       const int s = pair / p.KC, kc = pair - s * p.KC;
@@ -397,22 +457,30 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       const int* toff = t_off + (which ? p.S * P : 0) + s * P;
       const unsigned short* trow = t_row + s * P;
       const int my_chunk = kc >> 3, kcl = kc & 7;
+      constexpr bool PREFETCH = (RC > 0 && RC <= 8);
+      constexpr int RCN = RC > 0 ? RC : 1;
+      uint4 raw[RCN], nxt[PREFETCH ? RCN : 1];
+      auto load_group = [&](uint4* dst, int li) {
+        const int g = blockIdx.x + li * gridDim.x;
+        const bool active = owner && s < min(p.S, p.B2 - g * p.S);
+        const __nv_bfloat16* gbase = p.src[which] + static_cast<size_t>(g) * (which ? gstride1 : gstride0) + coff;
+#pragma unroll
+        for (int k = 0; k < RC; ++k) {
+          const int px = slice + k * PS;
+          if (active && px < P) dst[k] = __ldg(reinterpret_cast<const uint4*>(gbase + toff[px]));
+        }
+      };
+      if (my_groups > 0) load_group(raw, 0);
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
         const int S_act = min(p.S, p.B2 - g * p.S);
         const bool active = owner && s < S_act;
-        const __nv_bfloat16* gbase = p.src[which] + static_cast<size_t>(g) * (which ? gstride1 : gstride0) + coff;
-        uint4 raw[RC_MAX];
-#pragma unroll
-        for (int k = 0; k < RC_MAX; ++k) {
-          const int px = slice + k * PS;
-          if (active && px < P) raw[k] = *reinterpret_cast<const uint4*>(gbase + toff[px]);
-        }
+        if (!PREFETCH && li > 0) load_group(raw, li);
         float sum[8], sq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; sq[j] = 0.0f; }
 #pragma unroll
-        for (int k = 0; k < RC_MAX; ++k) {
+        for (int k = 0; k < RC; ++k) {
           if (active && slice + k * PS < P) {
             float f[8];
             unpack8(raw[k], f);
@@ -420,26 +488,23 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
           }
         }
-        if (owner) {
-          float4* dst = reinterpret_cast<float4*>(s_scr + (static_cast<size_t>(slice) * pairs + pair) * 16);
-          dst[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
-          dst[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
-          dst[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
-          dst[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
-        }
+        if (owner) put_record(slice * pairs + pair, sum, sq);
         xform_bar();
         stat_reduce(0, S_act, pairs, PS);
         xform_bar();
+        if (PREFETCH && li + 1 < my_groups) load_group(nxt, li + 1);
+        float ca[8], cb[8];
+        if (active) gn_coeffs(s, kc * 8, ca, cb);
         for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
           const int stage = a_it % p.a_stages;
           if (a_it >= p.a_stages) mbar_wait(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
           if (active && chunk == my_chunk) {
             uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes) + kcl * p.R;
 #pragma unroll
-            for (int k = 0; k < RC_MAX; ++k) {
+            for (int k = 0; k < RC; ++k) {
               const int px = slice + k * PS;
               if (px < P) {
-                gn_apply(raw[k], s, kc * 8);
+                gn_apply(raw[k], ca, cb);
                 a4[trow[px]] = raw[k];
               }
             }
@@ -447,6 +512,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
           xform_bar();
           if (xt == 0) mbar_arrive(&bar_a_full[stage]);
+        }
+        if (PREFETCH) {
+#pragma unroll
+          for (int k = 0; k < RC; ++k) raw[k] = nxt[k];
         }
       }
     } else {
@@ -456,7 +525,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const int S_act = min(p.S, p.B2 - g * p.S);
         const __nv_bfloat16* gb0 = p.src[0] + static_cast<size_t>(g) * gstride0;
         const __nv_bfloat16* gb1 = p.nsrc > 1 ? p.src[1] + static_cast<size_t>(g) * gstride1 : gb0;
-        if (p.groups > 0) {
+        if (GNM != GNM_NONE) {
           // deterministic statistics: per-thread partial records reduced in a fixed order, in batches of samples
           const int spb = max(1, STAT_PAIRS / p.KC);
           for (int sb = 0; sb < S_act; sb += spb) {
@@ -477,7 +546,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
                 uint4 raw[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                  if (px + u * PS < P) raw[u] = *reinterpret_cast<const uint4*>(base + toff[px + u * PS]);
+                  if (px + u * PS < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + toff[px + u * PS]));
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                   if (px + u * PS < P) {
@@ -487,11 +556,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
                     for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
                   }
               }
-              float4* dst = reinterpret_cast<float4*>(s_scr + (static_cast<size_t>(slice) * pairs + pair) * 16);
-              dst[0] = make_float4(sum[0], sum[1], sum[2], sum[3]);
-              dst[1] = make_float4(sum[4], sum[5], sum[6], sum[7]);
-              dst[2] = make_float4(sq[0], sq[1], sq[2], sq[3]);
-              dst[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
+              put_record(slice * pairs + pair, sum, sq);
             }
             xform_bar();
             stat_reduce(sb, ns, pairs, PS);
@@ -511,14 +576,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int item = b0 + u * XFORM_THREADS;
-              if (item < items) raw[u] = *reinterpret_cast<const uint4*>(base + toff[item >> 3] + (item & 7) * 8);
+              if (item < items) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + toff[item >> 3] + (item & 7) * 8));
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int item = b0 + u * XFORM_THREADS;
               if (item < items) {
                 const int sp = item >> 3, kcl = item & 7;
-                if (p.groups > 0) gn_apply(raw[u], sp / P, chunk * 64 + kcl * 8);
+                if (GNM != GNM_NONE) {
+                  float ca[8], cb[8];
+                  gn_coeffs(sp / P, chunk * 64 + kcl * 8, ca, cb);
+                  gn_apply(raw[u], ca, cb);
+                }
                 a4[kcl * p.R + t_row[sp]] = raw[u];
               }
             }
@@ -598,9 +667,11 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   else RD_REQUIRE(op.H_out == (op.H_in + 1 - 3) / 2 + 1 && op.W_out == (op.W_in + 1 - 3) / 2 + 1, "conv: bad downsample output size");
   p.Cin = cin; p.KC = cin / 8; p.nchunks = cin / 64; p.N = op.C_out;
   p.groups = op.gn_groups; p.silu = op.gn_silu; p.eps = op.gn_eps;
+  p.gnm = GNM_NONE;
   if (p.groups > 0) {
     RD_REQUIRE(cin % p.groups == 0 && op.gn_gamma && op.gn_beta, "conv: bad GroupNorm arguments");
     p.cpg = cin / p.groups;  // groups may straddle the concat boundary (192 ch / 32 groups): stats are per channel
+    p.gnm = (p.cpg % 8 == 0) ? GNM_CPG8 : (p.cpg == 4 ? GNM_CPG4 : GNM_GENERAL);
   }
   p.gamma = op.gn_gamma; p.beta = op.gn_beta;
   p.w = static_cast<const __nv_bfloat16*>(op.w);
@@ -637,12 +708,13 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
       if (conv_smem_layout(c).total > smem_cap && c.a_stages == 3) c.a_stages = 2;
       if (conv_smem_layout(c).total > smem_cap) continue;
     }
-    // transform mode: register-cached when every (sample, chunk) pair gets a thread and <= RC_MAX pixels
+    // transform mode: register-cached when every (sample, chunk) pair gets a thread and <= 16 pixels
     c.xmode = 0; c.rc_PS = 1;
     if (p.groups > 0 && c.S * p.KC <= XFORM_THREADS) {
       int ps = XFORM_THREADS / (c.S * p.KC);
       if (ps > p.H * p.W) ps = p.H * p.W;
-      if ((p.H * p.W + ps - 1) / ps <= RC_MAX) { c.xmode = 1; c.rc_PS = ps; }
+      const int slots = (p.H * p.W + ps - 1) / ps;
+      if (slots <= 16) { c.xmode = slots <= 8 ? 8 : 16; c.rc_PS = ps; }
     }
     double score = static_cast<double>(c.S * valid_px) / (nt * 128);
     if (c.acc_bufs == 1) score *= 0.75;
@@ -659,18 +731,40 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   return RD_OK;
 }
 
+typedef void (*conv_kernel_t)(const ConvParams);
+
+static conv_kernel_t conv_pick(int gnm, int rc) {
+#define RD_K(G, R) conv_gemm_kernel<G, R>
+  switch (gnm * 100 + rc) {
+    case GNM_NONE * 100 + 0: return RD_K(GNM_NONE, 0);
+    case GNM_CPG8 * 100 + 0: return RD_K(GNM_CPG8, 0);
+    case GNM_CPG8 * 100 + 8: return RD_K(GNM_CPG8, 8);
+    case GNM_CPG8 * 100 + 16: return RD_K(GNM_CPG8, 16);
+    case GNM_CPG4 * 100 + 0: return RD_K(GNM_CPG4, 0);
+    case GNM_CPG4 * 100 + 8: return RD_K(GNM_CPG4, 8);
+    case GNM_CPG4 * 100 + 16: return RD_K(GNM_CPG4, 16);
+    case GNM_GENERAL * 100 + 0: return RD_K(GNM_GENERAL, 0);
+    case GNM_GENERAL * 100 + 8: return RD_K(GNM_GENERAL, 8);
+    case GNM_GENERAL * 100 + 16: return RD_K(GNM_GENERAL, 16);
+    default: return nullptr;
+  }
+#undef RD_K
+}
+
 int conv_launch(const rd_op_conv& op, cudaStream_t st) {
   ConvParams p;
   int smem = 0, grid = 0;
   int rc = conv_make_params(op, p, smem, grid);
   if (rc != RD_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  conv_kernel_t k = conv_pick(p.gnm, p.xmode);
+  if (!k) return fail(RD_E_STATE, "conv: no kernel for gnm=%d rc=%d", p.gnm, p.xmode);
+  static bool configured[4][17] = {};
+  if (!configured[p.gnm][p.xmode]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+    configured[p.gnm][p.xmode] = true;
   }
-  conv_gemm_kernel<<<grid, CONV_THREADS, smem, st>>>(p);
+  k<<<grid, CONV_THREADS, smem, st>>>(p);
   return check_launch("conv_gemm_kernel");
 }
 
