@@ -121,6 +121,7 @@ typedef struct rd_op_conv {
   const float* bias;          /* [C_out] (sum of all fused biases) */
   const float* tproj;         /* [B2, tproj_stride] per-sample additive term or NULL */
   int32_t tproj_stride, tproj_off;
+  int32_t tproj_wrap;         /* >0: samples with index > tproj_wrap read row tproj_wrap (shared unconditional CFG row) */
   const void* residual;       /* bf16 NHWC [B2,H_out,W_out,C_out] identity skip or NULL */
   float out_scale;            /* 1/sqrt(2) when skip_rescale, else 1 */
   void* out;                  /* bf16 NHWC [B2,H_out,W_out,C_out] */
@@ -189,6 +190,8 @@ int rd_plan_run_range(rd_plan* p, int first, int count, void* stream);
 int rd_plan_destroy(rd_plan* p);
 /* shared-memory bytes / CTAs a conv op will launch with (planner feedback, also validates the op) */
 int rd_conv_launch_info(const rd_op_conv* op, int* smem_bytes, int* grid, int* rows_alloc);
+/* developer aid: CTA 0 of subsequent conv launches records clock64() stamps [3 roles][groups][8 points] into buf (NULL disables) */
+int rd_conv_set_trace(long long* buf, int groups);
 
 /* ---------------------------------------------------------------- whole sampler (sampling.py:292-339) */
 typedef struct rd_sampler_desc {

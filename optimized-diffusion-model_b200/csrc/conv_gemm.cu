@@ -11,11 +11,14 @@
 // Design (B200-first, nothing like the reference's cuDNN calls):
 //   * PERSISTENT kernel, one CTA per SM, looping over groups of S whole samples (GroupNorm statistics
 //     never leave the CTA).  16 warps with fixed roles that overlap through mbarrier pipelines:
-//       warp 0        MMA issuer (one elected thread, tcgen05.mma M=128 x N=C_out x K=16)
-//       warp 1        weight producer (1-D bulk TMA copies from L2; whole filter resident in shared
-//                     memory when it fits, else a ring recycled by tcgen05.commit)
+//       warp 0        MMA issuer (one elected thread, tcgen05.mma M=128 x N=C_out x K=16); the whole filter is
+//                     fetched once per CTA by this thread when it fits in shared memory
+//       warp 1        weight producer when the filter is streamed instead (1-D bulk TMA copies from L2 through
+//                     a ring recycled by tcgen05.commit)
 //       warps 4-7     epilogue: TMEM -> registers (tcgen05.ld 32x32b) -> bias/temb/skip -> bf16 NHWC
 //       warps 2,3,8-15 transform: global bf16 -> GroupNorm statistics -> normalise + SiLU -> operand ring
+//     (Role placement is measured, not arbitrary: issuing MMAs from several warps, or moving the issuer /
+//     epilogue to other warp slots, was slower on B200 -- see DESIGN.md.)
 //     While the tensor core works on group g, the transform warps stage group g+1 and the epilogue
 //     warps drain group g-1 (double-buffered TMEM accumulators).
 //   * The operand image of a 64-channel chunk is staged ONCE as [8 k-chunks][R rows][8 ch] (K-major,
@@ -24,6 +27,7 @@
 //     address advanced by (dy*Wp+dx)*16 B: nine taps, no im2col, no data movement (validated on B200 by
 //     tools/probe_umma.cu).  Outputs at padding rows are computed and dropped.
 //   * All index arithmetic is group-invariant and tabulated once per CTA in shared memory.
+#include <cstdlib>
 #include <cstring>
 #include "rd_common.h"
 #include "rd_ptx.cuh"
@@ -63,6 +67,7 @@ struct ConvParams {
   int a_stages, a_stage_bytes;
   int w_resident, w_stages, w_slab_bytes, n_slabs;
   int acc_bufs;
+  int n_issuers;     // MMA-issuing warps (tiles are dealt round-robin)
   int xmode, rc_PS;  // transform mode: >0 = register-cached single pass (value = register slots, rc_PS pixel slices), 0 = streaming
   int gnm;
   int tmem_cols;     // power of two >= acc_bufs*n_tiles*N
@@ -73,11 +78,14 @@ struct ConvParams {
   const __nv_bfloat16* w;  // [nchunks][ntaps][8][N][8]
   const float* bias;
   const float* tproj;
-  int tproj_stride, tproj_off;
+  int tproj_stride, tproj_off, tproj_wrap;
   const __nv_bfloat16* residual;
   float out_scale;
   __nv_bfloat16* out;
   int B2;
+  long long* trace;  // optional clock64 trace buffer (CTA 0 only): [role 0..2][group li][point 0..7]
+  int trace_groups;
+  int debug;  // RD_CONV_DEBUG bit 0: skip transform work, bit 1: skip epilogue work, bit 2: skip MMAs (timing experiments only)
   unsigned char ymap[2][MAX_HW], xmap[2][MAX_HW];
 };
 
@@ -104,7 +112,19 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(const ConvParams& p) 
   return L;
 }
 
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU(y) = y*sigmoid(y) = h + h*tanh(h) with h = y/2.  The GroupNorm affine is pre-halved when SiLU follows, so the
+// transform costs FFMA + MUFU.TANH + FFMA per channel.  tanh.approx.f32 has 2^-11 relative error, a quarter of the
+// bf16 rounding that follows.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+#define RD_TRACE(role, li, pt)                                                                                   \
+  do {                                                                                                          \
+    if (p.trace && blockIdx.x == 0 && (li) < p.trace_groups) p.trace[((role) * p.trace_groups + (li)) * 8 + (pt)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void xform_bar() { asm volatile("bar.sync 1, %0;" ::"n"(XFORM_THREADS) : "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
@@ -158,9 +178,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 
   // ------------------------------------------------------------------ setup
   if (tid == 0) {
-    for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], 1); }
-    for (int i = 0; i < MAX_W_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
+    for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], p.n_issuers); }
+    for (int i = 0; i < MAX_W_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], p.n_issuers); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], p.n_issuers); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
@@ -193,77 +213,108 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   if (warp == 0) {
     // ================================================================ MMA issuer
     if (elect_one()) {
+      const int iw = 0, n_iss = 1;
       // Descriptors are built once; per MMA only the 14-bit start-address field (units of 16 B == staged
-      // rows) is advanced, so the issue loop is a couple of integer adds per tcgen05.mma.
-      const uint32_t idesc = umma_idesc_bf16(128, p.N);
-      const uint32_t desc_hi = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
+      // rows) is advanced.  Every kernel parameter the loop needs is copied to a register first: reads of the
+      // parameter bank inside the loop (forced by the asm memory clobbers) cost tens of cycles each in a
+      // single-thread instruction stream and were the bottleneck of this role.
+      const int N = p.N, n_tiles = p.n_tiles, ntaps = p.ntaps, nchunks = p.nchunks, Wp = p.Wp;
+      const int a_stages = p.a_stages, w_stages = p.w_stages, acc_bufs = p.acc_bufs;
+      const bool w_resident = p.w_resident != 0, skip_mma = (p.debug & 4) != 0;
+      const uint32_t idesc = umma_idesc_bf16(128, N);
+      const uint64_t desc_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
       const uint32_t a_lo0 = (smem_u32(As) >> 4) | (static_cast<uint32_t>(p.R) << 16);  // LBO = R*16 B
-      const uint32_t w_lo0 = (smem_u32(Ws) >> 4) | (static_cast<uint32_t>(p.N) << 16);  // LBO = N*16 B
+      const uint32_t w_lo0 = (smem_u32(Ws) >> 4) | (static_cast<uint32_t>(N) << 16);    // LBO = N*16 B
       const uint32_t a_stage_u = p.a_stage_bytes >> 4, w_slab_u = p.w_slab_bytes >> 4;
-      const uint32_t kstep_a = 2 * p.R, kstep_w = 2 * p.N;
+      const uint32_t kstep_a = 2 * p.R, kstep_w = 2 * N;
+      const uint32_t acc_stride = n_tiles * N;
       int a_it = 0, w_it = 0;
-      if (p.w_resident && my_groups > 0) { mbar_wait(&bar_w_full[0], 0); tc_fence_after_sync(); }
+      if (w_resident && my_groups > 0) {
+        if (iw == 0) {  // the resident filter is fetched once per CTA
+          const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
+          mbar_arrive_expect_tx(&bar_w_full[0], p.n_slabs * p.w_slab_bytes);
+          for (int sidx = 0; sidx < p.n_slabs; ++sidx)
+            bulk_g2s(Ws + sidx * p.w_slab_bytes, wg + static_cast<size_t>(sidx) * p.w_slab_bytes, p.w_slab_bytes, &bar_w_full[0]);
+        }
+        mbar_wait(&bar_w_full[0], 0);
+        tc_fence_after_sync();
+      }
       for (int li = 0; li < my_groups; ++li) {
-        const int buf = li % p.acc_bufs, useb = li / p.acc_bufs;
+        const int buf = li % acc_bufs, useb = li / acc_bufs;
+        if (iw == 0) RD_TRACE(0, li, 0);
         if (useb > 0) { mbar_wait(&bar_acc_empty[buf], (useb - 1) & 1); tc_fence_after_sync(); }
-        const uint32_t acc = tmem + buf * p.n_tiles * p.N;
-        for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
-          const int stage = a_it % p.a_stages;
-          mbar_wait(&bar_a_full[stage], (a_it / p.a_stages) & 1);
+        if (iw == 0) RD_TRACE(0, li, 1);
+        const uint32_t acc = tmem + buf * acc_stride;
+        for (int chunk = 0; chunk < nchunks; ++chunk, ++a_it) {
+          const int stage = a_it % a_stages;
+          mbar_wait(&bar_a_full[stage], (a_it / a_stages) & 1);
           tc_fence_after_sync();
+          if (chunk == 0 && iw == 0) RD_TRACE(0, li, 2);
           const uint32_t a_lo_stage = a_lo0 + stage * a_stage_u;
           int shift = 0, col = 0;
-          for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int tap = 0; tap < ntaps; ++tap) {
             uint32_t w_lo;
             int ws = 0;
-            if (p.w_resident) {
-              w_lo = w_lo0 + (chunk * p.ntaps + tap) * w_slab_u;
+            if (w_resident) {
+              w_lo = w_lo0 + (chunk * ntaps + tap) * w_slab_u;
             } else {
-              ws = w_it % p.w_stages;
-              mbar_wait(&bar_w_full[ws], (w_it / p.w_stages) & 1);
+              ws = w_it % w_stages;
+              mbar_wait(&bar_w_full[ws], (w_it / w_stages) & 1);
               tc_fence_after_sync();
               w_lo = w_lo0 + ws * w_slab_u;
             }
-            uint32_t a_lo = a_lo_stage + shift;
+            const uint32_t a_lo = a_lo_stage + shift;
+            const uint32_t accum = (chunk | tap) != 0;
+            if (!skip_mma) {
+              if (N <= 64) {
+                // narrow N: keep the tiles of one k-step together
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | w_lo;
-              uint32_t a_t = a_lo, d_t = acc;
-              for (int tile = 0; tile < p.n_tiles; ++tile) {
-                umma_bf16_ss(d_t, (static_cast<uint64_t>(desc_hi) << 32) | a_t, db, idesc, (chunk | tap | kk) != 0);
-                a_t += 128;
-                d_t += p.N;
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t db = desc_hi | (w_lo + kk * kstep_w);
+                  const uint32_t a_k = a_lo + kk * kstep_a;
+#pragma unroll
+                  for (int tt = 0; tt < 4; ++tt) {
+                    const int tile = iw + tt * n_iss;
+                    if (tile < n_tiles) umma_bf16_ss(acc + tile * N, desc_hi | (a_k + tile * 128), db, idesc, accum | (kk != 0));
+                  }
+                }
+              } else {
+                // N >= 128: the four k-steps of a tile back to back on the same accumulator (65 vs 86 cycles per
+                // MMA on B200, tools/probe_umma2.cu)
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt) {
+                  const int tile = iw + tt * n_iss;
+                  if (tile < n_tiles) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                      umma_bf16_ss(acc + tile * N, desc_hi | (a_lo + tile * 128 + kk * kstep_a), desc_hi | (w_lo + kk * kstep_w), idesc,
+                                   accum | (kk != 0));
+                  }
+                }
               }
-              a_lo += kstep_a;
-              w_lo += kstep_w;
             }
-            if (!p.w_resident) { umma_commit(&bar_w_empty[ws]); ++w_it; }
+            if (!w_resident) { umma_commit(&bar_w_empty[ws]); ++w_it; }
             // next tap: (dy,dx) -> row shift dy*Wp + dx
-            if (++col == 3) { col = 0; shift += p.Wp - 2; } else { shift += 1; }
+            if (++col == 3) { col = 0; shift += Wp - 2; } else { shift += 1; }
           }
           umma_commit(&bar_a_empty[stage]);  // operand stage reusable once these MMAs have read it
         }
         umma_commit(&bar_acc_full[buf]);
+        if (iw == 0) RD_TRACE(0, li, 3);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================================================================ weight producer
-    if (lane == 0 && my_groups > 0) {
+    // ================================================================ weight producer (streamed filters only)
+    if (lane == 0 && my_groups > 0 && !p.w_resident) {
       const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
-      if (p.w_resident) {
-        mbar_arrive_expect_tx(&bar_w_full[0], p.n_slabs * p.w_slab_bytes);
-        for (int sidx = 0; sidx < p.n_slabs; ++sidx)
-          bulk_g2s(Ws + sidx * p.w_slab_bytes, wg + static_cast<size_t>(sidx) * p.w_slab_bytes, p.w_slab_bytes, &bar_w_full[0]);
-      } else {
-        const int total = my_groups * p.n_slabs;
-        for (int it = 0; it < total; ++it) {
-          const int ws = it % p.w_stages;
-          if (it >= p.w_stages) mbar_wait(&bar_w_empty[ws], ((it / p.w_stages) - 1) & 1);
-          mbar_arrive_expect_tx(&bar_w_full[ws], p.w_slab_bytes);
-          bulk_g2s(Ws + ws * p.w_slab_bytes, wg + static_cast<size_t>(it % p.n_slabs) * p.w_slab_bytes, p.w_slab_bytes,
-                   &bar_w_full[ws]);
-        }
+      const int total = my_groups * p.n_slabs;
+      for (int it = 0; it < total; ++it) {
+        const int ws = it % p.w_stages;
+        if (it >= p.w_stages) mbar_wait(&bar_w_empty[ws], ((it / p.w_stages) - 1) & 1);
+        mbar_arrive_expect_tx(&bar_w_full[ws], p.w_slab_bytes);
+        bulk_g2s(Ws + ws * p.w_slab_bytes, wg + static_cast<size_t>(it % p.n_slabs) * p.w_slab_bytes, p.w_slab_bytes,
+                 &bar_w_full[ws]);
       }
     }
     __syncwarp();
@@ -274,26 +325,63 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     const int cblocks = p.N / 32;
     const int nblocks = p.n_tiles * cblocks;
     const size_t out_gstride = static_cast<size_t>(p.S) * p.Ho * p.Wo * p.N;
+    constexpr int BTR = 8;  // (sample, channel) terms a thread carries in registers; the rest is loaded synchronously
+    float btv[BTR];
+    auto bt_value = [&](int g, int i) {
+      const int s = i / p.N, c = i - s * p.N;
+      float v = __ldg(p.bias + c);
+      if (p.tproj) {
+        int row = g * p.S + s;
+        if (p.tproj_wrap > 0 && row > p.tproj_wrap) row = p.tproj_wrap;  // shared unconditional-CFG row
+        v += __ldg(p.tproj + static_cast<size_t>(row) * p.tproj_stride + p.tproj_off + c);
+      }
+      return v * p.out_scale;
+    };
+    auto bt_load = [&](float (&v)[BTR], int g) {
+      const int n = min(p.S, p.B2 - g * p.S) * p.N;
+#pragma unroll
+      for (int k = 0; k < BTR; ++k) {
+        const int i = et + k * EPI_WARPS * 32;
+        if (i < n) v[k] = bt_value(g, i);
+      }
+    };
+    auto bt_store = [&](const float (&v)[BTR], float* dst, int g) {
+      const int n = min(p.S, p.B2 - g * p.S) * p.N;
+#pragma unroll
+      for (int k = 0; k < BTR; ++k) {
+        const int i = et + k * EPI_WARPS * 32;
+        if (i < n) dst[i] = v[k];
+      }
+      for (int i = et + BTR * EPI_WARPS * 32; i < n; i += EPI_WARPS * 32) dst[i] = bt_value(g, i);
+    };
     for (int li = 0; li < my_groups; ++li) {
       const int g = blockIdx.x + li * gridDim.x;
       const int sample0 = g * p.S;
       const int S_act = min(p.S, p.B2 - sample0);
       const int buf = li % p.acc_bufs;
-      // per-(sample, channel) additive term (bias + Dense_0(SiLU(temb))) * out_scale, staged while the MMAs run
+      // per-(sample, channel) additive term (bias + Dense_0(SiLU(temb))) * out_scale, staged through shared memory.
+      // The values of the NEXT group are fetched into registers here and stored after this group's body, so the
+      // global-load latency hides behind the accumulator wait.
       float* bt = s_bt + (li & 1) * p.S * p.N;
-      for (int i = et; i < S_act * p.N; i += EPI_WARPS * 32) {
-        const int s = i / p.N, c = i - s * p.N;
-        float v = __ldg(p.bias + c);
-        if (p.tproj) v += __ldg(p.tproj + static_cast<size_t>(sample0 + s) * p.tproj_stride + p.tproj_off + c);
-        bt[i] = v * p.out_scale;
+      if (li == 0) {
+        bt_load(btv, g);
+        bt_store(btv, bt, g);
       }
+      if (et == 0) RD_TRACE(1, li, 0);
       epi_bar();
+      if (et == 0) RD_TRACE(1, li, 1);
+      const bool have_next = li + 1 < my_groups;
+      if (have_next) bt_load(btv, g + gridDim.x);
       mbar_wait(&bar_acc_full[buf], (li / p.acc_bufs) & 1);
       tc_fence_after_sync();
+      if (et == 0) RD_TRACE(1, li, 2);
       const uint32_t acc = tmem + buf * p.n_tiles * p.N + (static_cast<uint32_t>(q * 32) << 16);
       __nv_bfloat16* og = p.out + static_cast<size_t>(g) * out_gstride;
       const __nv_bfloat16* rg = p.residual ? p.residual + static_cast<size_t>(g) * out_gstride : nullptr;
       const int valid_limit = S_act * p.Ho * p.Wo * p.N;
+      const bool skip_ld = (p.debug & 16) != 0;
+      const int N = p.N;
+      const float oscale = p.out_scale;
       uint4 res[4];
       {  // residual prefetch for block 0
         const int orow = t_orow[q * 32 + lane];
@@ -306,9 +394,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const int tile = blk / cblocks, c0 = (blk - tile * cblocks) * 32;
         const int row = tile * 128 + q * 32 + lane;
         const int orow = t_orow[row];
-        const bool valid = orow >= 0 && orow < valid_limit;
+        const bool valid = orow >= 0 && orow < valid_limit && !(p.debug & 2);
         uint32_t v[32];
-        tmem_ld32(acc + tile * p.N + c0, v);
+        if (!skip_ld) tmem_ld32(acc + tile * N + c0, v);
         uint4 cur[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur[j] = res[j];
@@ -320,22 +408,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rg + nor + nc0 + 8 * j);
           }
         }
-        tmem_ld_wait();
+        if (!skip_ld) tmem_ld_wait();
         if (valid) {
-          const float* btr = bt + t_os[row] * p.N + c0;
+          const float* btr = bt + t_os[row] * N + c0;
           uint4 outv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b0 = *reinterpret_cast<const float4*>(btr + 8 * j), b1 = *reinterpret_cast<const float4*>(btr + 8 * j + 4);
-            float a[8] = {fmaf(__uint_as_float(v[8 * j]), p.out_scale, b0.x), fmaf(__uint_as_float(v[8 * j + 1]), p.out_scale, b0.y),
-                          fmaf(__uint_as_float(v[8 * j + 2]), p.out_scale, b0.z), fmaf(__uint_as_float(v[8 * j + 3]), p.out_scale, b0.w),
-                          fmaf(__uint_as_float(v[8 * j + 4]), p.out_scale, b1.x), fmaf(__uint_as_float(v[8 * j + 5]), p.out_scale, b1.y),
-                          fmaf(__uint_as_float(v[8 * j + 6]), p.out_scale, b1.z), fmaf(__uint_as_float(v[8 * j + 7]), p.out_scale, b1.w)};
+            float a[8] = {fmaf(__uint_as_float(v[8 * j]), oscale, b0.x), fmaf(__uint_as_float(v[8 * j + 1]), oscale, b0.y),
+                          fmaf(__uint_as_float(v[8 * j + 2]), oscale, b0.z), fmaf(__uint_as_float(v[8 * j + 3]), oscale, b0.w),
+                          fmaf(__uint_as_float(v[8 * j + 4]), oscale, b1.x), fmaf(__uint_as_float(v[8 * j + 5]), oscale, b1.y),
+                          fmaf(__uint_as_float(v[8 * j + 6]), oscale, b1.z), fmaf(__uint_as_float(v[8 * j + 7]), oscale, b1.w)};
             if (rg) {
               float r[8];
               unpack8(cur[j], r);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = fmaf(r[e], p.out_scale, a[e]);
+              for (int e = 0; e < 8; ++e) a[e] = fmaf(r[e], oscale, a[e]);
             }
             outv[j] = pack8(a);
           }
@@ -347,6 +435,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+      if (et == 0) RD_TRACE(1, li, 3);
+      if (have_next) bt_store(btv, s_bt + ((li + 1) & 1) * p.S * p.N, g + gridDim.x);
     }
   } else {
     // ================================================================ transform (warps 2,3,8..15)
@@ -397,7 +487,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           cb[j] = fmaf(-mr.x, ca[j], bet[j]);
         }
       }
+      if (p.silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ca[j] *= 0.5f; cb[j] *= 0.5f; }
+      }
     };
+    // (ca, cb) are pre-halved by gn_coeffs when SiLU follows: h = y/2, SiLU(y) = h + h*tanh(h)
     auto gn_apply = [&](uint4& raw, const float (&ca)[8], const float (&cb)[8]) {
       float f[8];
       unpack8(raw, f);
@@ -405,7 +500,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], ca[j], cb[j]);
       if (p.silu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], tanh_approx(f[j]), f[j]);
       }
       raw = pack8(f);
     };
@@ -462,7 +557,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       uint4 raw[RCN], nxt[PREFETCH ? RCN : 1];
       auto load_group = [&](uint4* dst, int li) {
         const int g = blockIdx.x + li * gridDim.x;
-        const bool active = owner && s < min(p.S, p.B2 - g * p.S);
+        const bool active = owner && s < min(p.S, p.B2 - g * p.S) && !(p.debug & 1);
         const __nv_bfloat16* gbase = p.src[which] + static_cast<size_t>(g) * (which ? gstride1 : gstride0) + coff;
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
@@ -474,7 +569,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
         const int S_act = min(p.S, p.B2 - g * p.S);
-        const bool active = owner && s < S_act;
+        const bool active = owner && s < S_act && !(p.debug & 1);
+        if (xt == 0) RD_TRACE(2, li, 0);
         if (!PREFETCH && li > 0) load_group(raw, li);
         float sum[8], sq[8];
 #pragma unroll
@@ -488,16 +584,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
           }
         }
+        if (!(p.debug & 32)) {
         if (owner) put_record(slice * pairs + pair, sum, sq);
+        if (xt == 0) RD_TRACE(2, li, 1);
         xform_bar();
+        if (xt == 0) RD_TRACE(2, li, 2);
         stat_reduce(0, S_act, pairs, PS);
         xform_bar();
+        }
+        if (xt == 0) RD_TRACE(2, li, 3);
         if (PREFETCH && li + 1 < my_groups) load_group(nxt, li + 1);
         float ca[8], cb[8];
         if (active) gn_coeffs(s, kc * 8, ca, cb);
         for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
           const int stage = a_it % p.a_stages;
           if (a_it >= p.a_stages) mbar_wait(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
+          if (xt == 0 && chunk == 0) RD_TRACE(2, li, 4);
           if (active && chunk == my_chunk) {
             uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes) + kcl * p.R;
 #pragma unroll
@@ -509,9 +611,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               }
             }
           }
-          fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
+          if (xt == 0 && chunk == 0) RD_TRACE(2, li, 5);
+          if (!(p.debug & 8)) fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
+          if (xt == 0 && chunk == 0) RD_TRACE(2, li, 6);
           xform_bar();
           if (xt == 0) mbar_arrive(&bar_a_full[stage]);
+          if (xt == 0 && chunk == 0) RD_TRACE(2, li, 7);
         }
         if (PREFETCH) {
 #pragma unroll
@@ -631,6 +736,9 @@ static int conv_num_sms() {
   return sms;
 }
 
+static long long* g_trace = nullptr;
+static int g_trace_groups = 0;
+
 // Fills the launch geometry for an op; returns RD_OK or an error.
 int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& grid) {
   RD_REQUIRE(op.nsrc == 1 || op.nsrc == 2, "conv: nsrc must be 1 or 2");
@@ -675,9 +783,15 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   }
   p.gamma = op.gn_gamma; p.beta = op.gn_beta;
   p.w = static_cast<const __nv_bfloat16*>(op.w);
-  p.bias = op.bias; p.tproj = op.tproj; p.tproj_stride = op.tproj_stride; p.tproj_off = op.tproj_off;
+  p.bias = op.bias; p.tproj = op.tproj; p.tproj_stride = op.tproj_stride; p.tproj_off = op.tproj_off; p.tproj_wrap = op.tproj_wrap;
   p.residual = static_cast<const __nv_bfloat16*>(op.residual);
   p.out_scale = op.out_scale; p.out = static_cast<__nv_bfloat16*>(op.out); p.B2 = op.B2;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("RD_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+    p.trace = g_trace; p.trace_groups = g_trace_groups;
+  }
   p.w_slab_bytes = p.N * 128;
   p.n_slabs = p.nchunks * p.ntaps;
 
@@ -724,6 +838,7 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   RD_REQUIRE(best_score > 0, "conv: no tile geometry fits (Cin=%d N=%d rps=%d)", cin, p.N, p.rps);
   p = best;
   p.n_groups = (op.B2 + p.S - 1) / p.S;
+  p.n_issuers = 1;
   p.tmem_cols = next_pow2_cols(p.acc_bufs * p.n_tiles * p.N);
   smem_bytes = conv_smem_layout(p).total;
   const int sms = conv_num_sms();
@@ -769,6 +884,12 @@ int conv_launch(const rd_op_conv& op, cudaStream_t st) {
 }
 
 }  // namespace rd
+
+extern "C" int rd_conv_set_trace(long long* buf, int groups) {
+  rd::g_trace = buf;
+  rd::g_trace_groups = groups;
+  return RD_OK;
+}
 
 extern "C" int rd_conv_launch_info(const rd_op_conv* op, int* smem_bytes, int* grid, int* rows_alloc) {
   RD_REQUIRE(op, "rd_conv_launch_info: null op");

@@ -85,9 +85,12 @@ int temb_launch(const rd_op_temb& op, cudaStream_t st) {
 __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B,
                                                       int B2, int Cin, int Cout, int H, int W) {
-  extern __shared__ float sw[];  // [Cout][Cin*9] + bias[Cout]
+  extern __shared__ float sw[];  // [Cin*9][Cout] (tap-major: lanes read consecutive output channels) + bias[Cout]
   const int wn = Cout * Cin * 9;
-  for (int i = threadIdx.x; i < wn; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < wn; i += blockDim.x) {
+    const int co = i / (Cin * 9), t = i - co * (Cin * 9);
+    sw[t * Cout + co] = w[i];
+  }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[wn + i] = bias[i];
   __syncthreads();
   const int KC = Cout / 8;
@@ -100,18 +103,24 @@ __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ 
     const int b2 = static_cast<int>(pix / (static_cast<size_t>(W) * H));
     const float* xb = x + static_cast<size_t>(b2 % B) * Cin * H * W;  // x.repeat(2,1,1,1)
     float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sw[wn + kc * 8 + j];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(sw + wn + kc * 8), b1 = *reinterpret_cast<const float4*>(sw + wn + kc * 8 + 4);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
     for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
         const int yy = yh + dy - 1;
         if (yy < 0 || yy >= H) continue;
+#pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const int xx = xw + dx - 1;
           if (xx < 0 || xx >= W) continue;
-          const float v = xb[(static_cast<size_t>(ci) * H + yy) * W + xx];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += v * sw[((kc * 8 + j) * Cin + ci) * 9 + dy * 3 + dx];
+          const float v = __ldg(xb + (static_cast<size_t>(ci) * H + yy) * W + xx);
+          const float* wp = sw + (ci * 9 + dy * 3 + dx) * Cout + kc * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
         }
       }
     uint32_t pk[4];
@@ -148,14 +157,18 @@ __global__ void __launch_bounds__(OH_THREADS) out_head_kernel(const __nv_bfloat1
                                                               int Cimg, int H, int W, int groups, int cfg, float eps) {
   extern __shared__ float sm[];
   const int P = H * W;
-  float* act = sm;                     // [P][C+1]
-  float* sw = act + P * (C + 1);       // [Cimg][C][9]
+  const int LD = C + 4;                // row stride: 16-B aligned, rows 4 banks apart -> conflict-free float4 reads
+  float* act = sm;                     // [P][LD]
+  float* sw = act + P * LD;            // [Cimg][9][C] (tap-major)
   float* gsum = sw + Cimg * C * 9;     // [groups][2]
   float* res = gsum + groups * 2;      // [2][Cimg][P]
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
   const int cpg = C / groups;
-  for (int i = tid; i < Cimg * C * 9; i += OH_THREADS) sw[i] = w[i];
+  for (int i = tid; i < Cimg * C * 9; i += OH_THREADS) {
+    const int co = i / (C * 9), r = i - co * C * 9, c = r / 9, t = r - c * 9;
+    sw[(co * 9 + t) * C + c] = w[i];
+  }
   const int npass = cfg ? 2 : 1;
   for (int pass = 0; pass < npass; ++pass) {
     const __nv_bfloat16* hb = h + static_cast<size_t>(b + pass * B) * P * C;
@@ -166,14 +179,14 @@ __global__ void __launch_bounds__(OH_THREADS) out_head_kernel(const __nv_bfloat1
     for (int i = tid; i < P * C / 2; i += OH_THREADS) {
       const float2 f = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(hb)[i]);
       const int px = (2 * i) / C, c = (2 * i) % C;
-      act[px * (C + 1) + c] = f.x;
-      act[px * (C + 1) + c + 1] = f.y;
+      act[px * LD + c] = f.x;
+      act[px * LD + c + 1] = f.y;
     }
     __syncthreads();
     for (int g = tid >> 5; g < groups; g += OH_THREADS / 32) {  // one warp per group
       float s = 0.0f, q = 0.0f;
       for (int i = tid & 31; i < P * cpg; i += 32) {
-        const float v = act[(i / cpg) * (C + 1) + g * cpg + (i % cpg)];
+        const float v = act[(i / cpg) * LD + g * cpg + (i % cpg)];
         s += v; q += v * v;
       }
 #pragma unroll
@@ -188,8 +201,8 @@ __global__ void __launch_bounds__(OH_THREADS) out_head_kernel(const __nv_bfloat1
     __syncthreads();
     for (int i = tid; i < P * C; i += OH_THREADS) {
       const int px = i / C, c = i % C, g = c / cpg;
-      const float v = (act[px * (C + 1) + c] - gsum[2 * g]) * gsum[2 * g + 1] * gamma[c] + beta[c];
-      act[px * (C + 1) + c] = silu_acc(v);
+      const float v = (act[px * LD + c] - gsum[2 * g]) * gsum[2 * g + 1] * gamma[c] + beta[c];
+      act[px * LD + c] = silu_acc(v);
     }
     __syncthreads();
     for (int i = tid; i < Cimg * P; i += OH_THREADS) {
@@ -201,11 +214,14 @@ __global__ void __launch_bounds__(OH_THREADS) out_head_kernel(const __nv_bfloat1
         for (int dx = 0; dx < 3; ++dx) {
           const int xx = x + dx - 1;
           if (xx < 0 || xx >= W) continue;
-          const float* a = act + (yy * W + xx) * (C + 1);
-          const float* ww = sw + co * C * 9 + dy * 3 + dx;
-          float part = 0.0f;
-          for (int c = 0; c < C; ++c) part += a[c] * ww[c * 9];
-          acc += part;
+          const float4* a = reinterpret_cast<const float4*>(act + (yy * W + xx) * LD);
+          const float4* ww = reinterpret_cast<const float4*>(sw + (co * 9 + dy * 3 + dx) * C);
+          float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+          for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 av = a[c4], wv = ww[c4];
+            p0 = fmaf(av.x, wv.x, p0); p1 = fmaf(av.y, wv.y, p1); p2 = fmaf(av.z, wv.z, p2); p3 = fmaf(av.w, wv.w, p3);
+          }
+          acc += (p0 + p1) + (p2 + p3);
         }
       }
       res[(pass * Cimg + co) * P + px] = acc;
@@ -224,10 +240,10 @@ __global__ void __launch_bounds__(OH_THREADS) out_head_kernel(const __nv_bfloat1
 
 int outhead_launch(const rd_op_outhead& op, cudaStream_t st) {
   RD_REQUIRE(op.h && op.gamma && op.beta && op.w && op.bias && op.score, "out_head: null pointer");
-  RD_REQUIRE(op.groups > 0 && op.C % op.groups == 0 && op.C % 2 == 0, "out_head: bad GroupNorm geometry");
+  RD_REQUIRE(op.groups > 0 && op.C % op.groups == 0 && op.C % 4 == 0, "out_head: bad GroupNorm geometry");
   RD_REQUIRE(op.cfg ? (op.B2 == 2 * op.B) : (op.B2 == op.B), "out_head: B2 must be 2B with cfg, B otherwise");
   const int P = op.H * op.W;
-  const int smem = (P * (op.C + 1) + op.C_img * op.C * 9 + op.groups * 2 + 2 * op.C_img * P) * 4;
+  const int smem = (P * (op.C + 4) + op.C_img * op.C * 9 + op.groups * 2 + 2 * op.C_img * P) * 4;
   static int configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     RD_REQUIRE(smem <= 227 * 1024, "out_head: image too large for shared memory");

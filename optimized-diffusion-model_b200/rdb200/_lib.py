@@ -43,6 +43,7 @@ SIGNATURES = {
     "rd_plan_run_range": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "rd_plan_destroy": (C.c_int, [c_vp]),
     "rd_conv_launch_info": (C.c_int, [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rd_conv_set_trace": (C.c_int, [c_vp, C.c_int]),
     "rd_sampler_create": (C.c_int, [c_vp, C.POINTER(c_vp)]),
     "rd_sampler_run": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "rd_sampler_launches_per_iter": (C.c_int, [c_vp]),

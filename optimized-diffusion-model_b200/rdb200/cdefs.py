@@ -17,7 +17,7 @@ class OpConv(C.Structure):
         ("src", ConvSrc * 2), ("nsrc", i32), ("H_in", i32), ("W_in", i32), ("pad", i32), ("stride", i32),
         ("H_out", i32), ("W_out", i32), ("ntaps", i32), ("C_out", i32), ("gn_groups", i32), ("gn_silu", i32),
         ("gn_eps", C.c_float), ("gn_gamma", vp), ("gn_beta", vp), ("w", vp), ("bias", vp), ("tproj", vp),
-        ("tproj_stride", i32), ("tproj_off", i32), ("residual", vp), ("out_scale", C.c_float), ("out", vp),
+        ("tproj_stride", i32), ("tproj_off", i32), ("tproj_wrap", i32), ("residual", vp), ("out_scale", C.c_float), ("out", vp),
         ("B2", i32), ("samples_per_cta", i32)]
 
 

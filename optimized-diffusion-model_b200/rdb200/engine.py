@@ -112,6 +112,8 @@ class Engine:
         self.temb_dim = spec.nf * 4
         self.table_rows = 0
         self.time_table: Optional[torch.Tensor] = None
+        # CFG: the unconditional half shares label 0 and (inside the sampler) sigma, hence one temb row (index B)
+        self.temb_rows = self.B2
         self.tproj = torch.empty((self.B2, weights.n_dense_out), dtype=torch.float32, device=dev)
         self.acts: List[_Act] = []
         self._keep: List[object] = []
@@ -159,6 +161,7 @@ class Engine:
         c.w, c.bias = self.w.ptr(wname), self.w.ptr(bias)
         if tproj_off is not None:
             c.tproj, c.tproj_stride, c.tproj_off = self.tproj.data_ptr(), self.w.n_dense_out, tproj_off
+            c.tproj_wrap = self.B if self.temb_rows == self.B + 1 else 0
         if residual is not None:
             c.residual = residual.ptr
         c.out_scale, c.out, c.B2, c.samples_per_cta = out_scale, out.ptr, self.B2, 0
@@ -208,7 +211,7 @@ class Engine:
         t.labels = self.labels2.data_ptr() if sp.conditional else None
         t.dense_w, t.dense_b, t.out = w.ptr("dense.weight"), w.ptr("dense.bias"), self.tproj.data_ptr()
         t.step_ctr, t.row_idx = self.step_ctr.data_ptr(), None
-        t.B2, t.temb_dim, t.num_classes, t.n_out_total = self.B2, self.temb_dim, (sp.num_classes if sp.conditional else 0), w.n_dense_out
+        t.B2, t.temb_dim, t.num_classes, t.n_out_total = self.temb_rows, self.temb_dim, (sp.num_classes if sp.conditional else 0), w.n_dense_out
         self._temb_op = op
         # -- input conv
         op_in = D.Op()
@@ -333,6 +336,8 @@ class SamplerEngine(Engine):
 
     def __init__(self, spec, weights, B, H, W, device, sde, eps, snr, n_corrector_steps, cfg=True):
         super().__init__(spec, weights, B, H, W, cfg=cfg, device=device)
+        if cfg:
+            self.temb_rows = B + 1  # rows 0..B-1 conditional, row B shared by the whole unconditional half
         self.sde, self.eps, self.snr, self.n_corr = sde, eps, snr, n_corrector_steps
         self.N = sde.N
         t, sigma, g = sde.step_tables(eps)
