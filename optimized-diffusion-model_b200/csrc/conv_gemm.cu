@@ -68,6 +68,7 @@ struct ConvParams {
   int w_resident, w_stages, w_slab_bytes, n_slabs;
   int acc_bufs;
   int n_issuers;     // MMA-issuing warps (tiles are dealt round-robin)
+  int cluster;       // CTAs per thread-block cluster sharing the streamed filter by TMA multicast (1 = no cluster)
   int xmode, rc_PS;  // transform mode: >0 = register-cached single pass (value = register slots, rc_PS pixel slices), 0 = streaming
   int gnm;
   int tmem_cols;     // power of two >= acc_bufs*n_tiles*N
@@ -172,14 +173,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = p.H * p.W;
-  const int my_groups = (p.n_groups > static_cast<int>(blockIdx.x))
+  // Clustered launches walk the filter ring in lock step, so every CTA runs the same number of rounds; a round
+  // whose group index is past the end is a dummy (no samples: S_act <= 0, nothing staged, nothing stored).
+  const int my_groups = p.cluster > 1 ? (p.n_groups + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                        : (p.n_groups > static_cast<int>(blockIdx.x))
                             ? (p.n_groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
                             : 0;
+  const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1);
 
   // ------------------------------------------------------------------ setup
   if (tid == 0) {
     for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], p.n_issuers); }
-    for (int i = 0; i < MAX_W_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], p.n_issuers); }
+    for (int i = 0; i < MAX_W_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], p.n_issuers * p.cluster); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], p.n_issuers); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
     fence_mbar_init();
   }
@@ -207,6 +213,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // peers' barriers must be initialised before anything is multicast to them
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
@@ -221,6 +228,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       const int N = p.N, n_tiles = p.n_tiles, ntaps = p.ntaps, nchunks = p.nchunks, Wp = p.Wp;
       const int a_stages = p.a_stages, w_stages = p.w_stages, acc_bufs = p.acc_bufs;
       const bool w_resident = p.w_resident != 0, skip_mma = (p.debug & 4) != 0;
+      const int cl = p.cluster;
       const uint32_t idesc = umma_idesc_bf16(128, N);
       const uint64_t desc_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
       const uint32_t a_lo0 = (smem_u32(As) >> 4) | (static_cast<uint32_t>(p.R) << 16);  // LBO = R*16 B
@@ -228,6 +236,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       const uint32_t a_stage_u = p.a_stage_bytes >> 4, w_slab_u = p.w_slab_bytes >> 4;
       const uint32_t kstep_a = 2 * p.R, kstep_w = 2 * N;
       const uint32_t acc_stride = n_tiles * N;
+      const int tap0 = (w_resident || ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
       int a_it = 0, w_it = 0;
       if (w_resident && my_groups > 0) {
         if (iw == 0) {  // the resident filter is fetched once per CTA
@@ -251,8 +260,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           tc_fence_after_sync();
           if (chunk == 0 && iw == 0) RD_TRACE(0, li, 2);
           const uint32_t a_lo_stage = a_lo0 + stage * a_stage_u;
-          int shift = 0, col = 0;
-          for (int tap = 0; tap < ntaps; ++tap) {
+          // Streamed filters: every CTA walks the taps of a chunk in its own rotation, so that the 148 CTAs do
+          // not all pull the same 16 KB slab out of the same L2 slices at the same moment.
+          int tap = tap0;
+          int shift = (ntaps == 9) ? (tap / 3) * Wp + (tap % 3) : 0, col = tap % 3;
+          for (int tcount = 0; tcount < ntaps; ++tcount) {
             uint32_t w_lo;
             int ws = 0;
             if (w_resident) {
@@ -264,7 +276,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               w_lo = w_lo0 + ws * w_slab_u;
             }
             const uint32_t a_lo = a_lo_stage + shift;
-            const uint32_t accum = (chunk | tap) != 0;
+            const uint32_t accum = (chunk | tcount) != 0;
             if (!skip_mma) {
               if (N <= 64) {
                 // narrow N: keep the tiles of one k-step together
@@ -293,9 +305,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
                 }
               }
             }
-            if (!w_resident) { umma_commit(&bar_w_empty[ws]); ++w_it; }
-            // next tap: (dy,dx) -> row shift dy*Wp + dx
-            if (++col == 3) { col = 0; shift += Wp - 2; } else { shift += 1; }
+            if (!w_resident) {
+              if (cl > 1) umma_commit_multicast(&bar_w_empty[ws], cmask); else umma_commit(&bar_w_empty[ws]);
+              ++w_it;
+            }
+            // next tap: (dy,dx) -> row shift dy*Wp + dx, wrapping around after the last tap
+            if (++tap == ntaps) { tap = 0; col = 0; shift = 0; }
+            else if (++col == 3) { col = 0; shift += Wp - 2; } else { shift += 1; }
           }
           umma_commit(&bar_a_empty[stage]);  // operand stage reusable once these MMAs have read it
         }
@@ -309,12 +325,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     if (lane == 0 && my_groups > 0 && !p.w_resident) {
       const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
       const int total = my_groups * p.n_slabs;
+      const int tap0 = (p.ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
       for (int it = 0; it < total; ++it) {
         const int ws = it % p.w_stages;
         if (it >= p.w_stages) mbar_wait(&bar_w_empty[ws], ((it / p.w_stages) - 1) & 1);
         mbar_arrive_expect_tx(&bar_w_full[ws], p.w_slab_bytes);
-        bulk_g2s(Ws + ws * p.w_slab_bytes, wg + static_cast<size_t>(it % p.n_slabs) * p.w_slab_bytes, p.w_slab_bytes,
-                 &bar_w_full[ws]);
+        const int sl = it % p.n_slabs;  // position in this CTA's (rotated) order -> actual slab
+        const int chunk = sl / p.ntaps, tap = (sl - chunk * p.ntaps + tap0) % p.ntaps;
+        const unsigned char* src = wg + static_cast<size_t>(chunk * p.ntaps + tap) * p.w_slab_bytes;
+        if (p.cluster > 1) {
+          // every CTA of the cluster fetches 1/cluster of the slab and multicasts it to all of them
+          const uint32_t part = p.w_slab_bytes / p.cluster;
+          bulk_g2s_multicast(Ws + ws * p.w_slab_bytes + crank * part, src + crank * part, part, &bar_w_full[ws], cmask);
+        } else {
+          bulk_g2s(Ws + ws * p.w_slab_bytes, src, p.w_slab_bytes, &bar_w_full[ws]);
+        }
       }
     }
     __syncwarp();
@@ -357,7 +382,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     for (int li = 0; li < my_groups; ++li) {
       const int g = blockIdx.x + li * gridDim.x;
       const int sample0 = g * p.S;
-      const int S_act = min(p.S, p.B2 - sample0);
+      const int S_act = max(0, min(p.S, p.B2 - sample0));
       const int buf = li % p.acc_bufs;
       // per-(sample, channel) additive term (bias + Dense_0(SiLU(temb))) * out_scale, staged through shared memory.
       // The values of the NEXT group are fetched into registers here and stored after this group's body, so the
@@ -387,7 +412,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const int orow = t_orow[q * 32 + lane];
         if (rg && orow >= 0 && orow < valid_limit) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rg + orow + 8 * j);
+          for (int j = 0; j < 2; ++j) {
+            const u32x8 t = ld_global_256(rg + orow + 16 * j);
+            res[2 * j] = make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]);
+            res[2 * j + 1] = make_uint4(t.v[4], t.v[5], t.v[6], t.v[7]);
+          }
         }
       }
       for (int blk = 0; blk < nblocks; ++blk) {
@@ -405,7 +434,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           const int nor = t_orow[nt * 128 + q * 32 + lane];
           if (nor >= 0 && nor < valid_limit) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rg + nor + nc0 + 8 * j);
+            for (int j = 0; j < 2; ++j) {
+              const u32x8 t = ld_global_256(rg + nor + nc0 + 16 * j);
+              res[2 * j] = make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]);
+              res[2 * j + 1] = make_uint4(t.v[4], t.v[5], t.v[6], t.v[7]);
+            }
           }
         }
         if (!skip_ld) tmem_ld_wait();
@@ -427,9 +460,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             }
             outv[j] = pack8(a);
           }
-          uint4* dst = reinterpret_cast<uint4*>(og + orow + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = outv[j];
+          for (int j = 0; j < 2; ++j) {
+            u32x8 t;
+            t.v[0] = outv[2 * j].x; t.v[1] = outv[2 * j].y; t.v[2] = outv[2 * j].z; t.v[3] = outv[2 * j].w;
+            t.v[4] = outv[2 * j + 1].x; t.v[5] = outv[2 * j + 1].y; t.v[6] = outv[2 * j + 1].z; t.v[7] = outv[2 * j + 1].w;
+            st_global_256(og + orow + c0 + 16 * j, t);
+          }
         }
       }
       tc_fence_before_sync();
@@ -568,7 +605,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       if (my_groups > 0) load_group(raw, 0);
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
-        const int S_act = min(p.S, p.B2 - g * p.S);
+        const int S_act = max(0, min(p.S, p.B2 - g * p.S));
         const bool active = owner && s < S_act && !(p.debug & 1);
         if (xt == 0) RD_TRACE(2, li, 0);
         if (!PREFETCH && li > 0) load_group(raw, li);
@@ -627,7 +664,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       // ---------------- streaming mode: optional statistics pass, then a copy/normalise pass per chunk
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
-        const int S_act = min(p.S, p.B2 - g * p.S);
+        const int S_act = max(0, min(p.S, p.B2 - g * p.S));
         const __nv_bfloat16* gb0 = p.src[0] + static_cast<size_t>(g) * gstride0;
         const __nv_bfloat16* gb1 = p.nsrc > 1 ? p.src[1] + static_cast<size_t>(g) * gstride1 : gb0;
         if (GNM != GNM_NONE) {
@@ -707,6 +744,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 
   tc_fence_before_sync();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers
   if (warp == 0) tmem_dealloc(tmem, p.tmem_cols);
 }
 
@@ -839,10 +877,22 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   p = best;
   p.n_groups = (op.B2 + p.S - 1) / p.S;
   p.n_issuers = 1;
+  p.cluster = 1;
+  if (!p.w_resident) {
+    static int want = -1;
+    // EXPERIMENTAL, opt-in: measured no gain on B200 (the filter stream is latency-, not bandwidth-bound) and the
+    // 2-CTA variant does not yet pass the parity tests; kept as groundwork, never enabled by default.
+    if (want < 0) { const char* e = getenv("RD_CONV_CLUSTER"); want = e ? atoi(e) : 1; }
+    if ((want == 2 || want == 4) && p.w_slab_bytes % (16 * want) == 0) p.cluster = want;
+  }
   p.tmem_cols = next_pow2_cols(p.acc_bufs * p.n_tiles * p.N);
   smem_bytes = conv_smem_layout(p).total;
   const int sms = conv_num_sms();
   grid = p.n_groups < sms ? p.n_groups : sms;
+  if (p.cluster > 1) {
+    grid = grid / p.cluster * p.cluster;
+    if (grid == 0) { p.cluster = 1; grid = p.n_groups < sms ? p.n_groups : sms; }
+  }
   return RD_OK;
 }
 
@@ -879,7 +929,39 @@ int conv_launch(const rd_op_conv& op, cudaStream_t st) {
     if (e != cudaSuccess) return fail(static_cast<int>(e), "conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured[p.gnm][p.xmode] = true;
   }
-  k<<<grid, CONV_THREADS, smem, st>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(CONV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // Streamed filters are re-read by every CTA for every group: keep them persisting in L2 while the (much
+  // larger, read-once) activations stream through it.
+  static int l2_persist = -1;
+  if (l2_persist < 0) {
+    const char* ev = getenv("RD_CONV_L2_PERSIST");
+    l2_persist = ev ? atoi(ev) : 1;
+    if (l2_persist) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 32u << 20) != cudaSuccess) { l2_persist = 0; (void)cudaGetLastError(); }
+    }
+  }
+  if (l2_persist && !p.w_resident) {
+    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[1].val.accessPolicyWindow.base_ptr = const_cast<void*>(static_cast<const void*>(p.w));
+    attr[1].val.accessPolicyWindow.num_bytes = static_cast<size_t>(p.n_slabs) * p.w_slab_bytes;
+    attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.numAttrs = 2;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, p);
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "conv_gemm_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("conv_gemm_kernel");
 }
 
