@@ -94,7 +94,8 @@ enum rd_op_kind {
   RD_OP_ATTN_CORE = 2, /* softmax(q k^T / sqrt(C)) v per sample */
   RD_OP_TEMB = 3,      /* per-sample Dense_0(SiLU(temb)) for every ResBlock */
   RD_OP_IN_CONV = 4,   /* 3x3 conv C_in(=channels) -> nf from the fp32 state x */
-  RD_OP_OUT_HEAD = 5   /* GN + SiLU + 3x3 conv nf -> channels, CFG combine, fp32 score */
+  RD_OP_OUT_HEAD = 5,  /* GN + SiLU + 3x3 conv nf -> channels, CFG combine, fp32 score */
+  RD_OP_ATTN_BLOCK = 6 /* whole AttnBlockpp fused: GN, q/k/v, softmax(qk^T)v, output projection, skip */
 };
 
 typedef struct rd_conv_src {
@@ -135,6 +136,19 @@ typedef struct rd_op_attn {
   int32_t B2, T, C;
 } rd_op_attn;
 
+typedef struct rd_op_attn_block {
+  const void* x;        /* bf16 NHWC [B2, T, C] */
+  void* out;            /* bf16 NHWC [B2, T, C] = (x + attn(x)) * out_scale */
+  const void* wqkv_t;   /* bf16 [3C][72]: rows = output channel of q|k|v, cols = input channel (padded to 72) */
+  const void* wproj_t;  /* bf16 [C][72]: NIN_3 transposed the same way */
+  const float* bqkv;    /* [3C] */
+  const float* bproj;   /* [C] */
+  const float* gamma;   /* GroupNorm_0 */
+  const float* beta;
+  int32_t B2, T, C, groups;
+  float eps, out_scale;
+} rd_op_attn_block;
+
 typedef struct rd_op_temb {
   const float* time_table; /* [n_steps, temb_dim] = time_mlp(fourier(log sigma_i)) + label_emb.bias */
   const float* label_w;    /* [temb_dim, num_classes] label_emb.weight */
@@ -174,6 +188,7 @@ typedef struct rd_op {
   union {
     rd_op_conv conv;
     rd_op_attn attn;
+    rd_op_attn_block attn_block;
     rd_op_temb temb;
     rd_op_inconv inconv;
     rd_op_outhead outhead;

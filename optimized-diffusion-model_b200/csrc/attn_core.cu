@@ -152,3 +152,269 @@ int attn_launch(const rd_op_attn& op, cudaStream_t st) {
 }
 
 }  // namespace rd
+
+// ================================================================================================
+// Fused attention block: GroupNorm -> q,k,v projections -> softmax(q k^T / sqrt(C)) v -> output
+// projection -> (x + h)/sqrt(2), one kernel, activations never leave the SM (AttnBlockpp.forward,
+// reference models/layerspp.py:80-96).  Persistent CTAs loop over samples; one warp owns 16 query
+// rows through the whole chain: the q and attention-output accumulators are re-used directly as the
+// A fragments of the next mma.sync GEMM (no shared-memory round trip), k and v go through shared
+// memory once.  Projection weights sit in shared memory for the CTA's lifetime.
+namespace rd {
+
+constexpr int AB_LD = 72;  // bf16 row stride (144 B): conflict-free 32-bit fragment loads and ldmatrix rows
+
+template <int T16>
+__global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                              const __nv_bfloat16* __restrict__ wqkv_t,   // [192][AB_LD]
+                                                              const __nv_bfloat16* __restrict__ wproj_t,  // [64][AB_LD]
+                                                              const float* __restrict__ bqkv, const float* __restrict__ bproj,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              int B2, int T, int groups, float eps, float scale, float out_scale) {
+  constexpr int TP = 16 * T16;
+  constexpr int C = ATT_C;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(smraw);  // [3C][AB_LD]
+  __nv_bfloat16* Wp = Wq + 3 * C * AB_LD;                       // [C][AB_LD]
+  // two per-sample buffers, each used twice: raw rows -> (dead after normalisation) -> values;
+  // normalised rows -> (dead once every warp holds its A fragments) -> keys.  62 KB per CTA = 3 CTAs per SM.
+  __nv_bfloat16* Xr = Wp + C * AB_LD;                           // raw input rows   [TP][AB_LD]
+  __nv_bfloat16* Vs = Xr;                                       // values (aliases Xr)
+  __nv_bfloat16* Xn = Xr + TP * AB_LD;                          // normalised rows  [TP][AB_LD]
+  __nv_bfloat16* Ks = Xn;                                       // keys (aliases Xn)
+  float* s_par = reinterpret_cast<float*>(Xn + TP * AB_LD);     // bqkv[3C], bproj[C], gamma[C], beta[C], chsum[2C], gstat[2*groups]
+  float* s_bq = s_par;
+  float* s_bp = s_bq + 3 * C;
+  float* s_ga = s_bp + C;
+  float* s_be = s_ga + C;
+  float* s_cs = s_be + C;
+  float* s_gs = s_cs + 2 * C;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthr = blockDim.x;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int cpg = C / groups;
+
+  for (int i = tid; i < 3 * C * AB_LD / 8; i += nthr) reinterpret_cast<uint4*>(Wq)[i] = reinterpret_cast<const uint4*>(wqkv_t)[i];
+  for (int i = tid; i < C * AB_LD / 8; i += nthr) reinterpret_cast<uint4*>(Wp)[i] = reinterpret_cast<const uint4*>(wproj_t)[i];
+  for (int i = tid; i < 3 * C; i += nthr) s_bq[i] = bqkv[i];
+  for (int i = tid; i < C; i += nthr) { s_bp[i] = bproj[i]; s_ga[i] = gamma[i]; s_be[i] = beta[i]; }
+  // zero the padding rows once (rows >= T of Xn / Ks / Vs are never written afterwards)
+  for (int i = tid; i < (TP - T) * AB_LD / 2; i += nthr) {
+    const int off = T * AB_LD / 2 + i;
+    reinterpret_cast<uint32_t*>(Xn)[off] = 0u;
+    reinterpret_cast<uint32_t*>(Xr)[off] = 0u;
+  }
+  __syncthreads();
+
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  for (int b = blockIdx.x; b < B2; b += gridDim.x) {
+    const __nv_bfloat16* xb = x + static_cast<size_t>(b) * T * C;
+    // ---- raw rows -> shared memory (coalesced 16-byte chunks)
+    for (int i = tid; i < T * (C / 8); i += nthr) {
+      const int row = i >> 3, seg = i & 7;
+      *reinterpret_cast<uint4*>(Xr + row * AB_LD + seg * 8) = *reinterpret_cast<const uint4*>(xb + row * C + seg * 8);
+    }
+    __syncthreads();
+    // ---- GroupNorm statistics: per-channel sums, then per-group mean / rstd
+    for (int c = tid; c < C; c += nthr) {
+      float s1 = 0.0f, s2 = 0.0f;
+      for (int t = 0; t < T; ++t) {
+        const float v = __bfloat162float(Xr[t * AB_LD + c]);
+        s1 += v;
+        s2 = fmaf(v, v, s2);
+      }
+      s_cs[c] = s1;
+      s_cs[C + c] = s2;
+    }
+    __syncthreads();
+    if (tid < groups) {
+      float s1 = 0.0f, s2 = 0.0f;
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { s1 += s_cs[c]; s2 += s_cs[C + c]; }
+      const float inv = 1.0f / static_cast<float>(cpg * T);
+      const float mean = s1 * inv;
+      const float var = fmaxf(s2 * inv - mean * mean, 0.0f);
+      s_gs[2 * tid] = mean;
+      s_gs[2 * tid + 1] = 1.0f / sqrtf(var + eps);
+    }
+    __syncthreads();
+    for (int i = tid; i < T * (C / 2); i += nthr) {
+      const int row = i / (C / 2), c = (i - row * (C / 2)) * 2;
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Xr + row * AB_LD + c));
+      const int ga = c / cpg, gb = (c + 1) / cpg;
+      const float a = (v.x - s_gs[2 * ga]) * s_gs[2 * ga + 1] * s_ga[c] + s_be[c];
+      const float bb = (v.y - s_gs[2 * gb]) * s_gs[2 * gb + 1] * s_ga[c + 1] + s_be[c + 1];
+      *reinterpret_cast<uint32_t*>(Xn + row * AB_LD + c) = pack_bf16(a, bb);
+    }
+    __syncthreads();
+
+    // ---- q, k, v projections for this warp's 16 rows (A fragments straight from Xn)
+    uint32_t xa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const __nv_bfloat16* a0 = Xn + r0 * AB_LD + kk * 16 + 2 * q4;
+      const __nv_bfloat16* a1 = Xn + r1 * AB_LD + kk * 16 + 2 * q4;
+      xa[kk][0] = *reinterpret_cast<const uint32_t*>(a0);
+      xa[kk][1] = *reinterpret_cast<const uint32_t*>(a1);
+      xa[kk][2] = *reinterpret_cast<const uint32_t*>(a0 + 8);
+      xa[kk][3] = *reinterpret_cast<const uint32_t*>(a1 + 8);
+    }
+    __syncthreads();  // every warp holds its A fragments: Xn may now be overwritten with the keys (and Xr with the values)
+    auto project8 = [&](const uint32_t (&afrag)[4][4], const __nv_bfloat16* W, int nb, float (&acc)[4]) {
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+      const __nv_bfloat16* wr = W + (nb * 8 + g) * AB_LD + 2 * q4;  // B fragment: (k = 2q..2q+1 [+8], n = g)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        mma_bf16_16816(acc, afrag[kk], *reinterpret_cast<const uint32_t*>(wr + kk * 16), *reinterpret_cast<const uint32_t*>(wr + kk * 16 + 8));
+    };
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      float c0[4], c1[4];
+      project8(xa, Wq, 2 * kk, c0);
+      project8(xa, Wq, 2 * kk + 1, c1);
+      const int ca = (2 * kk) * 8 + 2 * q4, cb = (2 * kk + 1) * 8 + 2 * q4;
+      qa[kk][0] = pack_bf16(c0[0] + s_bq[ca], c0[1] + s_bq[ca + 1]);
+      qa[kk][1] = pack_bf16(c0[2] + s_bq[ca], c0[3] + s_bq[ca + 1]);
+      qa[kk][2] = pack_bf16(c1[0] + s_bq[cb], c1[1] + s_bq[cb + 1]);
+      qa[kk][3] = pack_bf16(c1[2] + s_bq[cb], c1[3] + s_bq[cb + 1]);
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      float ck[4], cv[4];
+      project8(xa, Wq, 8 + nb, ck);
+      project8(xa, Wq, 16 + nb, cv);
+      const int c = nb * 8 + 2 * q4;
+      if (r0 < T) {
+        *reinterpret_cast<uint32_t*>(Ks + r0 * AB_LD + c) = pack_bf16(ck[0] + s_bq[C + c], ck[1] + s_bq[C + c + 1]);
+        *reinterpret_cast<uint32_t*>(Vs + r0 * AB_LD + c) = pack_bf16(cv[0] + s_bq[2 * C + c], cv[1] + s_bq[2 * C + c + 1]);
+      }
+      if (r1 < T) {
+        *reinterpret_cast<uint32_t*>(Ks + r1 * AB_LD + c) = pack_bf16(ck[2] + s_bq[C + c], ck[3] + s_bq[C + c + 1]);
+        *reinterpret_cast<uint32_t*>(Vs + r1 * AB_LD + c) = pack_bf16(cv[2] + s_bq[2 * C + c], cv[3] + s_bq[2 * C + c + 1]);
+      }
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T, softmax over the T valid keys
+    float s[2 * T16][4];
+#pragma unroll
+    for (int nb = 0; nb < 2 * T16; ++nb) {
+      s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.0f;
+      const __nv_bfloat16* kr = Ks + (nb * 8 + g) * AB_LD + 2 * q4;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        mma_bf16_16816(s[nb], qa[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16), *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < 2 * T16; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = (nb * 8 + 2 * q4 + e) < T;
+        s[nb][e] = ok ? s[nb][e] * scale : -INFINITY;
+        s[nb][2 + e] = ok ? s[nb][2 + e] * scale : -INFINITY;
+        m0 = fmaxf(m0, s[nb][e]);
+        m1 = fmaxf(m1, s[nb][2 + e]);
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+    for (int nb = 0; nb < 2 * T16; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nb][e] = __expf(s[nb][e] - m0);
+        s[nb][2 + e] = __expf(s[nb][2 + e] - m1);
+        l0 += s[nb][e];
+        l1 += s[nb][2 + e];
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+    // ---- O = P V
+    float o[C / 8][4];
+#pragma unroll
+    for (int nb = 0; nb < C / 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < T16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nb = 0; nb < C / 8; ++nb) {
+        uint32_t b0, b1;
+        const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(Vs + (kk * 16 + (lane & 15)) * AB_LD + nb * 8));
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+        mma_bf16_16816(o[nb], pa, b0, b1);
+      }
+    }
+    // ---- output projection: the normalised attention output is re-used as A fragments
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    uint32_t oa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      oa[kk][0] = pack_bf16(o[2 * kk][0] * i0, o[2 * kk][1] * i0);
+      oa[kk][1] = pack_bf16(o[2 * kk][2] * i1, o[2 * kk][3] * i1);
+      oa[kk][2] = pack_bf16(o[2 * kk + 1][0] * i0, o[2 * kk + 1][1] * i0);
+      oa[kk][3] = pack_bf16(o[2 * kk + 1][2] * i1, o[2 * kk + 1][3] * i1);
+    }
+    __nv_bfloat16* ob = out + static_cast<size_t>(b) * T * C;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      float y[4];
+      project8(oa, Wp, nb, y);
+      const int c = nb * 8 + 2 * q4;
+      if (r0 < T) {
+        const float2 xr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xb + r0 * C + c));  // residual from L2
+        *reinterpret_cast<uint32_t*>(ob + r0 * C + c) = pack_bf16((xr.x + y[0] + s_bp[c]) * out_scale, (xr.y + y[1] + s_bp[c + 1]) * out_scale);
+      }
+      if (r1 < T) {
+        const float2 xr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xb + r1 * C + c));
+        *reinterpret_cast<uint32_t*>(ob + r1 * C + c) = pack_bf16((xr.x + y[2] + s_bp[c]) * out_scale, (xr.y + y[3] + s_bp[c + 1]) * out_scale);
+      }
+    }
+    __syncthreads();  // Xr / Ks / Vs are overwritten by the next sample
+  }
+}
+
+int attn_block_launch(const rd_op_attn_block& op, cudaStream_t st) {
+  RD_REQUIRE(op.x && op.out && op.wqkv_t && op.wproj_t && op.bqkv && op.bproj && op.gamma && op.beta && op.B2 > 0,
+             "attn_block: null pointer / empty batch");
+  RD_REQUIRE(op.C == ATT_C, "attn_block: only C == %d is supported in this round (got %d)", ATT_C, op.C);
+  RD_REQUIRE(op.T >= 1 && op.T <= 128, "attn_block: T must be in [1,128] (got %d)", op.T);
+  RD_REQUIRE(op.groups > 0 && op.C % op.groups == 0, "attn_block: bad GroupNorm geometry");
+  const float scale = 1.0f / sqrtf(static_cast<float>(op.C));
+  const int t16 = (op.T + 15) / 16;
+  const int tp = 16 * t16;
+  const int smem = (4 * ATT_C * AB_LD + 2 * tp * AB_LD) * 2 + (3 * ATT_C + 3 * ATT_C + 2 * ATT_C + 2 * op.groups) * 4 + 64;
+  const int ctas_per_sm = 227 * 1024 / (smem + 1024) > 4 ? 4 : 227 * 1024 / (smem + 1024);
+  int grid = kNumSMs * (ctas_per_sm > 0 ? ctas_per_sm : 1);
+  if (grid > op.B2) grid = op.B2;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(op.x);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(op.out);
+  const __nv_bfloat16* wq = static_cast<const __nv_bfloat16*>(op.wqkv_t);
+  const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(op.wproj_t);
+  static bool configured[9] = {};
+  switch (t16) {
+#define RD_AB_CASE(n)                                                                                                              \
+  case n:                                                                                                                           \
+    if (!configured[n]) {                                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(attn_block_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);          \
+      if (e != cudaSuccess) return fail(static_cast<int>(e), "attn_block: %s", cudaGetErrorString(e));                              \
+      configured[n] = true;                                                                                                         \
+    }                                                                                                                               \
+    attn_block_kernel<n><<<grid, 32 * n, smem, st>>>(x, out, wq, wp, op.bqkv, op.bproj, op.gamma, op.beta, op.B2, op.T, op.groups,   \
+                                                     op.eps, scale, op.out_scale);                                                  \
+    break;
+    RD_AB_CASE(1) RD_AB_CASE(2) RD_AB_CASE(3) RD_AB_CASE(4) RD_AB_CASE(5) RD_AB_CASE(6) RD_AB_CASE(7) RD_AB_CASE(8)
+#undef RD_AB_CASE
+    default: return fail(RD_E_UNSUPPORTED, "attn_block: T=%d unsupported", op.T);
+  }
+  return check_launch("attn_block_kernel");
+}
+
+}  // namespace rd

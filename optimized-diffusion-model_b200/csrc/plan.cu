@@ -8,6 +8,7 @@
 namespace rd {
 int conv_launch(const rd_op_conv& op, cudaStream_t st);
 int attn_launch(const rd_op_attn& op, cudaStream_t st);
+int attn_block_launch(const rd_op_attn_block& op, cudaStream_t st);
 int temb_launch(const rd_op_temb& op, cudaStream_t st);
 int inconv_launch(const rd_op_inconv& op, cudaStream_t st);
 int outhead_launch(const rd_op_outhead& op, cudaStream_t st);
@@ -30,6 +31,7 @@ static int run_op(const rd_op& op, cudaStream_t st) {
   switch (op.kind) {
     case RD_OP_CONV: return conv_launch(op.u.conv, st);
     case RD_OP_ATTN_CORE: return attn_launch(op.u.attn, st);
+    case RD_OP_ATTN_BLOCK: return attn_block_launch(op.u.attn_block, st);
     case RD_OP_TEMB: return temb_launch(op.u.temb, st);
     case RD_OP_IN_CONV: return inconv_launch(op.u.inconv, st);
     case RD_OP_OUT_HEAD: return outhead_launch(op.u.outhead, st);

@@ -2,7 +2,7 @@
 tests/test_abi.py cross-checks sizeof/offsetof against a tiny C program compiled from the header)."""
 import ctypes as C
 
-RD_OP_CONV, RD_OP_ATTN_CORE, RD_OP_TEMB, RD_OP_IN_CONV, RD_OP_OUT_HEAD = 1, 2, 3, 4, 5
+RD_OP_CONV, RD_OP_ATTN_CORE, RD_OP_TEMB, RD_OP_IN_CONV, RD_OP_OUT_HEAD, RD_OP_ATTN_BLOCK = 1, 2, 3, 4, 5, 6
 
 i32 = C.c_int32
 vp = C.c_void_p
@@ -25,6 +25,12 @@ class OpAttn(C.Structure):
     _fields_ = [("qkv", vp), ("out", vp), ("B2", i32), ("T", i32), ("C", i32)]
 
 
+class OpAttnBlock(C.Structure):
+    _fields_ = [("x", vp), ("out", vp), ("wqkv_t", vp), ("wproj_t", vp), ("bqkv", vp), ("bproj", vp), ("gamma", vp),
+                ("beta", vp), ("B2", i32), ("T", i32), ("C", i32), ("groups", i32), ("eps", C.c_float),
+                ("out_scale", C.c_float)]
+
+
 class OpTemb(C.Structure):
     _fields_ = [("time_table", vp), ("label_w", vp), ("labels", vp), ("dense_w", vp), ("dense_b", vp), ("out", vp),
                 ("step_ctr", vp), ("row_idx", vp), ("B2", i32), ("temb_dim", i32), ("num_classes", i32),
@@ -43,7 +49,7 @@ class OpOutHead(C.Structure):
 
 
 class _OpUnion(C.Union):
-    _fields_ = [("conv", OpConv), ("attn", OpAttn), ("temb", OpTemb), ("inconv", OpInConv), ("outhead", OpOutHead)]
+    _fields_ = [("conv", OpConv), ("attn", OpAttn), ("attn_block", OpAttnBlock), ("temb", OpTemb), ("inconv", OpInConv), ("outhead", OpOutHead)]
 
 
 class Op(C.Structure):

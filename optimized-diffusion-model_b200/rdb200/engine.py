@@ -137,7 +137,7 @@ class Engine:
         check(lib().rd_plan_add(self.plan, C.byref(op)), f"rd_plan_add({name})")
         self.op_names.append(name)
         self.op_kinds[name] = {D.RD_OP_CONV: "conv", D.RD_OP_ATTN_CORE: "attn", D.RD_OP_TEMB: "temb",
-                               D.RD_OP_IN_CONV: "in_conv", D.RD_OP_OUT_HEAD: "out_head"}[op.kind]
+                               D.RD_OP_IN_CONV: "in_conv", D.RD_OP_OUT_HEAD: "out_head", D.RD_OP_ATTN_BLOCK: "attn_block"}[op.kind]
 
     def _conv(self, name, srcs, H_in, W_in, C_out, wname, bias, *, ntaps=9, pad=1, stride=1, gn=None, silu=1,
               tproj_off=None, residual=None, out_scale=1.0) -> _Act:
@@ -185,9 +185,25 @@ class Engine:
                           residual=short, out_scale=rs)
 
     def _attn(self, p: str, x: _Act) -> _Act:
-        """AttnBlockpp (layerspp.py:80-96): fused qkv projection, attention core, output projection + skip."""
+        """AttnBlockpp (layerspp.py:80-96).  Default: ONE fused kernel (GN, q/k/v, softmax(qk^T)v, projection, skip).
+        RD_ATTN_FUSED=0 selects the three-launch path (tcgen05 qkv projection, attention core, tcgen05 output
+        projection) that the fused kernel replaced; it is kept for A/B measurements."""
+        import os
         rs = float(1.0 / np.sqrt(2.0)) if self.spec.skip_rescale else 1.0
         Cc = x.C
+        if os.environ.get("RD_ATTN_FUSED", "1") != "0" and Cc == 64 and x.H * x.W <= 128:
+            out = self._act(x.H, x.W, Cc)
+            op = D.Op()
+            op.kind = D.RD_OP_ATTN_BLOCK
+            a = op.u.attn_block
+            a.x, a.out = x.ptr, out.ptr
+            a.wqkv_t, a.wproj_t = self.w.ptr(p + ".wqkv_t"), self.w.ptr(p + ".wproj_t")
+            a.bqkv, a.bproj = self.w.ptr(p + ".qkv.bias"), self.w.ptr(p + ".proj.bias")
+            a.gamma, a.beta = self.w.ptr(p + ".GroupNorm_0.weight"), self.w.ptr(p + ".GroupNorm_0.bias")
+            a.B2, a.T, a.C, a.groups, a.eps, a.out_scale = self.B2, x.H * x.W, Cc, min(Cc // 4, 32), 1e-6, rs
+            self._add(op, p)
+            self.tensors[p] = out
+            return out
         qkv = self._conv(p + ".qkv", [x], x.H, x.W, 3 * Cc, p + ".qkv.w", p + ".qkv.bias", ntaps=1, pad=0,
                          gn=p + ".GroupNorm_0", silu=0)
         a = self._act(x.H, x.W, Cc)

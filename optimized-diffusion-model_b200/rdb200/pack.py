@@ -29,6 +29,13 @@ def pack_1x1(W: torch.Tensor) -> torch.Tensor:
     return t.permute(0, 3, 1, 4, 2).contiguous().to(torch.bfloat16)
 
 
+def pad_rows(w: torch.Tensor, ld: int) -> torch.Tensor:
+    """[rows, cols] fp32 -> [rows, ld] bf16 with zero padding (shared-memory image of the mma.sync B operand)."""
+    out = torch.zeros((w.shape[0], ld), dtype=torch.bfloat16, device=w.device)
+    out[:, : w.shape[1]] = w.to(torch.bfloat16)
+    return out
+
+
 class PackedWeights:
     """Device-resident packed parameters of one NCSNpp instance."""
 
@@ -91,6 +98,9 @@ class PackedWeights:
             self._put(f"{p}.qkv.bias", torch.cat([f32(sd[f"{p}.NIN_{j}.b"]) for j in range(3)]))
             self._put(f"{p}.proj.w", pack_1x1(f32(sd[f"{p}.NIN_3.W"])))
             self._put(f"{p}.proj.bias", f32(sd[f"{p}.NIN_3.b"]))
+            # fused attention kernel: weights transposed to [out][in] bf16 rows padded to 72 (conflict-free fragments)
+            self._put(f"{p}.wqkv_t", pad_rows(qkv.t().contiguous(), 72))
+            self._put(f"{p}.wproj_t", pad_rows(f32(sd[f"{p}.NIN_3.W"]).t().contiguous(), 72))
         for k in list(sd.keys()):
             if (k.startswith("downsample.") or k.startswith("upsample.")) and k.endswith(".Conv_0.weight"):
                 p = k[: -len(".weight")]
