@@ -19,6 +19,11 @@
  *   rd_plan_* / rd_op         NCSNpp.forward and its layers        models/ncsnpp.py:226-354,
  *                                                                  models/layerspp.py:67-214, models/layers.py:531-540
  *   rd_sampler_*              get_pc_sampler / pc_sampler loop     sampling.py:292-339
+ * "next" rows (callers either side of the path):
+ *   rd_perturb_reflect_f32    x_t = cube.reflect(mean + std z)      losses.py:80-82
+ *   rd_dsm_reduce_f32         weighted squared error + reduce_op    losses.py:86-92
+ *   rd_pf_drift_f32           probability-flow drift * mollifier    sampling.py:345-383, sde_lib.py:93-101
+ *   rd_gto_halo_decode_f32    latent -> physical units              ../Benchmark/gto_halo_benchmarking.py:255-328, 335-363
  */
 #ifndef RDB200_H
 #define RDB200_H
@@ -84,6 +89,33 @@ int rd_pc_predictor_step(const float* x, const float* score, const float* z, con
 /* out = (1+w)*s_cond - w*s_uncond ; s is [2B, D] (cond first); w: [B] device or NULL -> w_scalar. */
 int rd_cfg_combine_f32(const float* s, const float* w, float w_scalar, float* out, size_t B, size_t D,
                        void* stream);
+
+/* ---------------------------------------------------------------- evaluation loss + codec ("next" rows) */
+/* out[b,:] = reflect(x0[b,:] + std[b] * z[b,:])  (product and sum rounded separately). */
+int rd_perturb_reflect_f32(const float* x0, const float* z, const float* std, float* out, size_t B, size_t D,
+                           void* stream);
+/* out[b] = scale * sum_d weight[b] * (score[b,d] - target[b,d])^2 ; scale = 1/D if reduce_mean else 0.5. */
+int rd_dsm_reduce_f32(const float* score, const float* target, const float* weight, float* out, size_t B, size_t D,
+                      int reduce_mean, void* stream);
+/* out = (0 - g^2 * score * 0.5) * bump(x); g: [B] device or NULL -> g_scalar;
+ * bump(x) = exp((-1/(0.25 - (0.5-x)^2) + 4) / moll) when moll > 0, else x. */
+int rd_pf_drift_f32(const float* x, const float* score, const float* g, float g_scalar, float moll, float* out,
+                    size_t B, size_t D, void* stream);
+/* Constants of the GTO-Halo un-normalisation; spans are (max - min). Row layout of a decoded sample:
+ * [halo energy | shooting time, 2 coast times | n_triplets x (alpha, beta, r) | fuel mass, halo period, manifold length]. */
+typedef struct rd_gto_halo_codec {
+  float data_mean, data_std;
+  float shooting_time_min, shooting_time_span;
+  float coast_time_min, coast_time_span;
+  float halo_energy_min, halo_energy_span;
+  float fuel_mass_min, fuel_mass_span;
+  float manifold_length_min, manifold_length_span;
+  float thrust;
+  int32_t n_triplets;
+} rd_gto_halo_codec;
+/* latents: [n, row_stride] fp32 (row 0 = class label, then the model variables); out: [n, 7 + 3 n_triplets]. */
+int rd_gto_halo_decode_f32(const float* latents, float* out, size_t n, size_t row_stride,
+                           const rd_gto_halo_codec* codec, void* stream);
 
 /* ---------------------------------------------------------------- NCSN++ forward as an op plan */
 /* The host (python, mirroring NCSNpp.__init__) lowers the network to a flat list of ops over

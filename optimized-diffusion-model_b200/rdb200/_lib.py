@@ -36,6 +36,10 @@ SIGNATURES = {
     "rd_pc_predictor_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_float, C.c_float, c_vp, c_vp, C.c_size_t,
                                        C.c_size_t, C.c_uint64, C.c_uint32, c_vp, C.c_size_t, C.c_int, C.c_int, c_vp]),
     "rd_cfg_combine_f32": (C.c_int, [c_vp, c_vp, C.c_float, c_vp, C.c_size_t, C.c_size_t, c_vp]),
+    "rd_perturb_reflect_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_size_t, C.c_size_t, c_vp]),
+    "rd_dsm_reduce_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_size_t, C.c_size_t, C.c_int, c_vp]),
+    "rd_pf_drift_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_float, C.c_float, c_vp, C.c_size_t, C.c_size_t, c_vp]),
+    "rd_gto_halo_decode_f32": (C.c_int, [c_vp, c_vp, C.c_size_t, C.c_size_t, c_vp, c_vp]),
     "rd_plan_create": (C.c_int, [C.POINTER(c_vp)]),
     "rd_plan_add": (C.c_int, [c_vp, c_vp]),
     "rd_plan_size": (C.c_int, [c_vp]),

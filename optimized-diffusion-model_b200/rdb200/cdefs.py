@@ -8,6 +8,13 @@ i32 = C.c_int32
 vp = C.c_void_p
 
 
+class GtoHaloCodec(C.Structure):
+    _fields_ = [(n, C.c_float) for n in (
+        "data_mean", "data_std", "shooting_time_min", "shooting_time_span", "coast_time_min", "coast_time_span",
+        "halo_energy_min", "halo_energy_span", "fuel_mass_min", "fuel_mass_span", "manifold_length_min",
+        "manifold_length_span", "thrust")] + [("n_triplets", i32)]
+
+
 class ConvSrc(C.Structure):
     _fields_ = [("ptr", vp), ("C", i32), ("Hs", i32), ("Ws", i32)]
 

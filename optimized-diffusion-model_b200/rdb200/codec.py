@@ -1,0 +1,61 @@
+"""Latent -> physical-unit codec of the GTO-Halo benchmark, the consumer directly downstream of the
+sampler (reference Benchmark/gto_halo_benchmarking.py:255-328 `generate_samples` tail and :335-363
+`_convert_to_spherical`).  One CUDA kernel, one thread per sample (csrc/next_rows.cu)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from ._lib import check, lib, ptr, require_cuda_f32, stream_ptr
+from .cdefs import GtoHaloCodec
+
+
+@dataclass
+class GtoHaloConstants:
+    """The constants hard-coded at gto_halo_benchmarking.py:266-280."""
+    data_mean: float = 0.4652
+    data_std: float = 0.1811
+    min_shooting_time: float = 0
+    max_shooting_time: float = 40
+    min_coast_time: float = 0
+    max_coast_time: float = 15
+    min_halo_energy: float = 0.008
+    max_halo_energy: float = 0.095
+    min_final_fuel_mass: float = 408
+    max_final_fuel_mass: float = 470
+    min_manifold_length: float = 5
+    max_manifold_length: float = 11
+    thrust: float = 1.0
+    n_variables: int = 67  # values kept per sample (label + 66 model outputs)
+
+    def c_struct(self) -> GtoHaloCodec:
+        n_ctrl = self.n_variables - 1 - 3 - 3
+        if n_ctrl < 0:
+            raise ValueError("n_variables must be at least 7")
+        return GtoHaloCodec(
+            self.data_mean, self.data_std,
+            self.min_shooting_time, self.max_shooting_time - self.min_shooting_time,
+            self.min_coast_time, self.max_coast_time - self.min_coast_time,
+            self.min_halo_energy, self.max_halo_energy - self.min_halo_energy,
+            self.min_final_fuel_mass, self.max_final_fuel_mass - self.min_final_fuel_mass,
+            self.min_manifold_length, self.max_manifold_length - self.min_manifold_length,
+            self.thrust, n_ctrl // 3)
+
+
+def gto_halo_decode(samples: torch.Tensor, consts: GtoHaloConstants = GtoHaloConstants()) -> torch.Tensor:
+    """samples: [N, ...] fp32 CUDA latents straight from the sampler (e.g. [N,1,9,9] or [N,1,8,9]);
+    returns [N, 7 + 3*n_triplets] physical variables on the same device.  Control variables that do not
+    fill a whole (ux,uy,uz) triplet are dropped, as in the reference (:295-298)."""
+    x = require_cuda_f32(samples, "samples")
+    n = x.shape[0]
+    stride = x.numel() // max(n, 1)
+    cs = consts.c_struct()
+    width = 7 + 3 * cs.n_triplets
+    if stride < consts.n_variables:
+        raise ValueError(f"samples carry {stride} values each; the codec needs {consts.n_variables}")
+    out = torch.empty((n, width), dtype=torch.float32, device=x.device)
+    check(lib().rd_gto_halo_decode_f32(ptr(x), ptr(out), n, stride, C.byref(cs), stream_ptr(x.device)),
+          "rd_gto_halo_decode_f32")
+    return out

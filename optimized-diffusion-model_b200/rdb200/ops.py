@@ -123,3 +123,51 @@ def predictor_step(x, score, z: Optional[torch.Tensor], g, N: int, seed: int = 0
                                      float(np.float32(np.sqrt(-dt))), ptr(x_out), ptr(x_mean), B, D, seed,
                                      draw_base, None, 0, 0, per_sample, stream_ptr(x.device)), "rd_pc_predictor_step")
     return x_out, x_mean
+
+
+def perturb_reflect(x0: torch.Tensor, z: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
+    """reflect(x0 + std[:, None] * z) -- the forward perturbation of the DSM loss (losses.py:80-82)."""
+    x0 = require_cuda_f32(x0, "x0")
+    z = require_cuda_f32(z, "z")
+    std = require_cuda_f32(std.to(x0.device), "std").reshape(-1)
+    if z.shape != x0.shape or std.numel() != x0.shape[0]:
+        raise ValueError("perturb_reflect: shape mismatch")
+    B = x0.shape[0]
+    out = torch.empty_like(x0)
+    check(lib().rd_perturb_reflect_f32(ptr(x0), ptr(z), ptr(std), ptr(out), B, x0.numel() // max(B, 1),
+                                       stream_ptr(x0.device)), "rd_perturb_reflect_f32")
+    return out
+
+
+def dsm_reduce(score: torch.Tensor, target: torch.Tensor, weight: torch.Tensor, reduce_mean: bool) -> torch.Tensor:
+    """[B] per-sample losses: reduce_op(weight[b] * (score - target)^2) (losses.py:86-92)."""
+    score = require_cuda_f32(score, "score")
+    target = require_cuda_f32(target, "target")
+    weight = require_cuda_f32(weight.to(score.device), "weight").reshape(-1)
+    if score.shape != target.shape or weight.numel() != score.shape[0]:
+        raise ValueError("dsm_reduce: shape mismatch")
+    B = score.shape[0]
+    out = torch.empty(B, dtype=torch.float32, device=score.device)
+    check(lib().rd_dsm_reduce_f32(ptr(score), ptr(target), ptr(weight), ptr(out), B, score.numel() // max(B, 1),
+                                  1 if reduce_mean else 0, stream_ptr(score.device)), "rd_dsm_reduce_f32")
+    return out
+
+
+def pf_drift(x: torch.Tensor, score: torch.Tensor, g, moll: float) -> torch.Tensor:
+    """Probability-flow drift of the reflected VE SDE times the boundary mollifier (sampling.py:345-383)."""
+    x = require_cuda_f32(x, "x")
+    score = require_cuda_f32(score, "score")
+    if x.shape != score.shape:
+        raise ValueError("pf_drift: shape mismatch")
+    B = x.shape[0]
+    if torch.is_tensor(g):
+        g_t = require_cuda_f32(g.reshape(-1).to(x.device), "g")
+        if g_t.numel() != B:
+            raise ValueError("g must have one entry per sample")
+        gp, gs = ptr(g_t), 0.0
+    else:
+        gp, gs = None, float(g)
+    out = torch.empty_like(x)
+    check(lib().rd_pf_drift_f32(ptr(x), ptr(score), gp, gs, float(moll), ptr(out), B, x.numel() // max(B, 1),
+                                stream_ptr(x.device)), "rd_pf_drift_f32")
+    return out

@@ -62,6 +62,7 @@ def get_sampling_fn(config, sde, shape, eps, device):
     s = config.sampling
     method = s.method.lower()
     if method == 'ode':
+        get_denoiser(s.denoiser.lower())  # looked up (and validated) before the sampler is built, like the reference
         return get_ode_sampler(sde=sde, shape=shape, eps=eps, moll=s.moll, side_eps=s.side_eps, device=device)
     if method == 'pc':
         return get_pc_sampler(sde=sde, shape=shape, predictor=get_predictor(s.predictor.lower()),
@@ -236,8 +237,35 @@ def _tape_iteration(pred, corr, x, vec_t, tape, device):
     return x
 
 
-def get_ode_sampler(sde, shape, denoise=False, rtol=1e-5, atol=1e-5, method='RK45', eps=1e-3, moll=1e-3, side_eps=1e-2,
-                    device='cuda'):
-    """Probability-flow ODE sampler (sampling.py:342-392) -- listed as a "next" row in SURVEY.md
-    section 8f; not part of the B200 hot path yet."""
-    raise NotImplementedError("the probability-flow ODE sampler is outside the B200 hot path (SURVEY.md 8f)")
+def get_ode_sampler(sde, shape, rtol=1e-5, atol=1e-5, method='RK45', eps=1e-3, moll=200, side_eps=1e-2, device='cuda'):
+    """Probability-flow ODE sampler with scipy's black-box solver (sampling.py:342-392).
+
+    Same host loop as the reference (the adaptive step control lives in `scipy.integrate.solve_ivp`, state
+    crosses the host boundary as flattened float64 on every evaluation); each right-hand side is one guided
+    network plan + one fused drift-times-mollifier kernel (csrc/next_rows.cu)."""
+    from scipy import integrate
+
+    def ode_sampler(model, z=None, noise_removal_model=None, weight=0, class_labels=None):
+        """-> (samples [B,C,H,W] on `device`, number of function evaluations)."""
+        with torch.no_grad():
+            if z is None:
+                x = (1 - 2 * side_eps) * torch.rand(shape).to(device) + side_eps
+            else:
+                x = z
+            if class_labels is None:
+                score_fn = mutils.get_score_fn(sde, model, train=False)
+            else:
+                score_fn = mutils.get_cf_score_fn(sde, model, class_labels, weight)
+
+            def ode_func(t, flat):
+                xt = from_flattened_numpy(flat, shape).to(device).type(torch.float32)
+                vec_t = torch.ones(shape[0], device=xt.device) * t
+                g = sde.sde(xt, vec_t)[1]
+                return to_flattened_numpy(_ops.pf_drift(xt, score_fn(xt, vec_t), g, moll))
+
+            solution = integrate.solve_ivp(ode_func, (sde.T, eps), to_flattened_numpy(x), rtol=rtol, atol=atol,
+                                           method=method)
+            x = torch.tensor(solution.y[:, -1]).reshape(shape).to(device).type(torch.float32)
+            return x, solution.nfev
+
+    return ode_sampler

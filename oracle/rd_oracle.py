@@ -462,3 +462,87 @@ def pc_sampler(score_fn, sched: VESchedule, scfg: SamplerConfig, x0: Tensor, noi
         if trace is not None:
             trace.append((i, x_c.clone(), x.clone()))
     return x
+
+
+# ----------------------------------------------------------------------------------------------
+# "next" rows: evaluation DSM loss, EMA, latent -> physical codec
+def dsm_loss(score_fn, sched: VESchedule, batch: Tensor, u: Tensor, z: Tensor, reduce_mean: bool = True,
+             likelihood_weighting: bool = True, eps: float = 1e-5):
+    """Evaluation loss (losses.py:77-92) with the two RNG draws passed in: `u` uniform [B] and `z`
+    like `batch`.  `score_fn(x, sigma)` is the (unguided) network call.  Returns (loss, per-sample
+    losses, perturbed data, heat-kernel target)."""
+    t = u * (sched.T - eps) + eps  # losses.py:78
+    std = sched.sigma(t)  # marginal_prob: mean = batch (sde_lib.py:141-143)
+    perturbed = reflect(batch + std[:, None, None, None] * z)
+    score = score_fn(perturbed, std)
+    target = score_hk(perturbed, batch, std)
+    w = sched.diffusion(t) ** 2 if likelihood_weighting else std ** 2
+    losses = w[:, None, None, None] * (score - target).pow(2)
+    flat = losses.reshape(losses.shape[0], -1)
+    per_sample = torch.mean(flat, dim=-1) if reduce_mean else 0.5 * torch.sum(flat, dim=-1)
+    return torch.mean(per_sample), per_sample, perturbed, target
+
+
+def ode_sampler(score_fn, sched: VESchedule, x0: Tensor, rtol: float = 1e-5, atol: float = 1e-5, method: str = "RK45",
+                moll: float = 200, eps: Optional[float] = None):
+    """Probability-flow ODE sampler (sampling.py:342-392): scipy solve_ivp over
+    drift(x,t) = -(g(t)^2 * score * 0.5) * bump(x).  `score_fn(x, sigma)`; returns (x, nfev)."""
+    from scipy import integrate
+    shape = tuple(x0.shape)
+    eps = sched.eps if eps is None else eps
+
+    def bump(x):
+        return ((-1 / (0.5 ** 2 - (0.5 - x).pow(2)) + 4) / moll).exp() if moll > 0 else x
+
+    def f(t, flat):
+        x = torch.from_numpy(flat.reshape(shape)).type(torch.float32)
+        vec_t = torch.ones(shape[0]) * t
+        g = sched.diffusion(vec_t)
+        drift = torch.zeros_like(x) - g[:, None, None, None] ** 2 * score_fn(x, sched.sigma(vec_t)) * 0.5
+        return (drift * bump(x)).detach().cpu().numpy().reshape((-1,))
+
+    sol = integrate.solve_ivp(f, (sched.T, eps), x0.detach().cpu().numpy().reshape((-1,)), rtol=rtol, atol=atol,
+                              method=method)
+    return torch.tensor(sol.y[:, -1]).reshape(shape).type(torch.float32), sol.nfev
+
+
+def ema_update(shadow: List[Tensor], params: List[Tensor], decay: float, num_updates: Optional[int]):
+    """One ExponentialMovingAverage.update (models/ema.py:32-52); returns the new num_updates."""
+    d = decay
+    if num_updates is not None:
+        num_updates += 1
+        d = min(d, (1 + num_updates) / (10 + num_updates))
+    for s, p in zip(shadow, params):
+        s.sub_((1.0 - d) * (s - p))
+    return num_updates
+
+
+def gto_halo_decode(samples: np.ndarray, n_variables: int = 67) -> np.ndarray:
+    """Latents -> physical units (Benchmark/gto_halo_benchmarking.py:255-328, :335-363), numpy fp32.
+    PARITY UNPINNED: the reference code is the tail of a method whose module imports the CR3BP/SNOPT
+    stack (not importable here), so this restatement is checked by reading, not against its outputs."""
+    s = np.asarray(samples, dtype=np.float32).reshape(samples.shape[0], -1)[:, :n_variables]
+    label = s[:, 0]
+    m = s[:, 1:] * np.float32(0.1811) + np.float32(0.4652)  # global mean/std un-normalisation (:266-268)
+    m[:, 0] = m[:, 0] * np.float32(40 - 0) + np.float32(0)
+    m[:, 1] = m[:, 1] * np.float32(15 - 0) + np.float32(0)
+    m[:, 2] = m[:, 2] * np.float32(15 - 0) + np.float32(0)
+    m[:, 3:-3] = m[:, 3:-3] * np.float32(2) * np.float32(1.0) - np.float32(1.0)
+    n_ctrl = (m.shape[1] - 6) // 3 * 3
+    c = m[:, 3:3 + n_ctrl].reshape(m.shape[0], -1, 3)
+    ux, uy, uz = c[:, :, 0].copy(), c[:, :, 1].copy(), c[:, :, 2].copy()
+    u = np.sqrt(ux ** 2 + uy ** 2 + uz ** 2)
+    theta = np.zeros_like(u)
+    nz = u != 0
+    theta[nz] = np.arcsin(uz[nz] / u[nz])
+    alpha = np.arctan2(uy, ux)
+    two_pi = np.float32(2 * np.pi)
+    alpha = np.where(alpha >= 0, alpha, two_pi + alpha)
+    theta = np.where(theta >= 0, theta, two_pi + theta)
+    u = np.minimum(u, np.float32(1))
+    c[:, :, 0], c[:, :, 1], c[:, :, 2] = alpha, theta, u
+    m[:, 3:3 + n_ctrl] = c.reshape(m.shape[0], n_ctrl)
+    m[:, -3] = m[:, -3] * np.float32(470 - 408) + np.float32(408)
+    m[:, -1] = m[:, -1] * np.float32(11 - 5) + np.float32(5)
+    halo = label * np.float32(0.095 - 0.008) + np.float32(0.008)
+    return np.column_stack((halo, m)).astype(np.float32)

@@ -39,6 +39,7 @@ def test_struct_layouts_match_the_c_compiler():
 int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rd_conv_src), sizeof(rd_op_conv), sizeof(rd_op_attn),
          sizeof(rd_op_temb), sizeof(rd_op_inconv), sizeof(rd_op_outhead), sizeof(rd_op), sizeof(rd_sampler_desc));
+  printf("%zu %zu %zu\n", sizeof(rd_op_attn_block), sizeof(rd_gto_halo_codec), offsetof(rd_gto_halo_codec, n_triplets));
   printf("%zu %zu %zu %zu %zu\n", offsetof(rd_op_conv, gn_gamma), offsetof(rd_op_conv, out), offsetof(rd_op, u),
          offsetof(rd_op_outhead, score), offsetof(rd_sampler_desc, seed));
   return 0;
@@ -52,6 +53,7 @@ int main(void) {
     sizes = [int(v) for v in out]
     mine = [C.sizeof(t) for t in (cdefs.ConvSrc, cdefs.OpConv, cdefs.OpAttn, cdefs.OpTemb, cdefs.OpInConv,
                                   cdefs.OpOutHead, cdefs.Op, cdefs.SamplerDesc)]
+    mine += [C.sizeof(cdefs.OpAttnBlock), C.sizeof(cdefs.GtoHaloCodec), cdefs.GtoHaloCodec.n_triplets.offset]
     mine += [cdefs.OpConv.gn_gamma.offset, cdefs.OpConv.out.offset, cdefs.Op.u.offset, cdefs.OpOutHead.score.offset,
              cdefs.SamplerDesc.seed.offset]
     assert sizes == mine
