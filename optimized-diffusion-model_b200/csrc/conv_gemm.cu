@@ -29,6 +29,7 @@
 //   * All index arithmetic is group-invariant and tabulated once per CTA in shared memory.
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include "rd_common.h"
 #include "rd_ptx.cuh"
 
@@ -149,6 +150,66 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// All MMAs of one filter tap over one 64-channel chunk: 4 k-steps x NT accumulator tiles.  NT is a compile-time
+// constant so that no MMA is predicated: with run-time tile counts ptxas re-materialises the (zero, idesc) and
+// descriptor-high uniform-register pairs for every instruction, and the single issuing thread -- whose uniform-
+// datapath instructions cost ~10 cycles each -- drops from the tensor core's 50 cycles per MMA to 70.
+template <int NT, bool TILE_OUTER>
+__device__ __forceinline__ void issue_tap(uint32_t acc, uint32_t N, uint32_t a_lo, uint32_t w_lo, uint32_t kstep_a,
+                                          uint32_t kstep_w, uint64_t desc_hi, uint32_t idesc, uint32_t accum) {
+  if (!TILE_OUTER) {
+    // narrow N: the tiles of one k-step together (they share the B descriptor)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint64_t db = desc_hi | (w_lo + kk * kstep_w);
+      const uint32_t a_k = a_lo + kk * kstep_a;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) umma_bf16_ss(acc + t * N, desc_hi | (a_k + t * 128), db, idesc, kk == 0 ? accum : 1u);
+    }
+  } else {
+    // N >= 128: the four k-steps of a tile back to back on the same accumulator (65 vs 86 cycles per MMA on
+    // B200, tools/probe_umma2.cu)
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_bf16_ss(acc + t * N, desc_hi | (a_lo + t * 128 + kk * kstep_a), desc_hi | (w_lo + kk * kstep_w), idesc,
+                     kk == 0 ? accum : 1u);
+    }
+  }
+}
+
+// Epilogue body for one block (32 accumulator columns of the row this thread owns): scale, add the staged
+// (bias + temb) row, optionally add the residual, convert to bf16 and store 64 contiguous bytes.
+__device__ __forceinline__ void epi_finish_block(const uint32_t (&v)[32], const float* __restrict__ btr, float oscale,
+                                                 const uint4* resv, __nv_bfloat16* dst, int dbg = 0) {
+  uint4 outv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 b0, b1;
+    if (dbg & 128) { b0 = make_float4(oscale, oscale, oscale, oscale); b1 = b0; }
+    else { b0 = *reinterpret_cast<const float4*>(btr + 8 * j); b1 = *reinterpret_cast<const float4*>(btr + 8 * j + 4); }
+    float a[8] = {fmaf(__uint_as_float(v[8 * j]), oscale, b0.x), fmaf(__uint_as_float(v[8 * j + 1]), oscale, b0.y),
+                  fmaf(__uint_as_float(v[8 * j + 2]), oscale, b0.z), fmaf(__uint_as_float(v[8 * j + 3]), oscale, b0.w),
+                  fmaf(__uint_as_float(v[8 * j + 4]), oscale, b1.x), fmaf(__uint_as_float(v[8 * j + 5]), oscale, b1.y),
+                  fmaf(__uint_as_float(v[8 * j + 6]), oscale, b1.z), fmaf(__uint_as_float(v[8 * j + 7]), oscale, b1.w)};
+    if (resv) {
+      float r[8];
+      unpack8(resv[j], r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = fmaf(r[e], oscale, a[e]);
+    }
+    outv[j] = pack8(a);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    u32x8 t;
+    t.v[0] = outv[2 * j].x; t.v[1] = outv[2 * j].y; t.v[2] = outv[2 * j].z; t.v[3] = outv[2 * j].w;
+    t.v[4] = outv[2 * j + 1].x; t.v[5] = outv[2 * j + 1].y; t.v[6] = outv[2 * j + 1].z; t.v[7] = outv[2 * j + 1].w;
+    if (!(dbg & 64) || t.v[0] == 0x12345678u) st_global_256(dst + 16 * j, t);
+  }
+}
+
 template <int GNM, int RC>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -219,46 +280,48 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 
   if (warp == 0) {
     // ================================================================ MMA issuer
-    if (elect_one()) {
-      const int iw = 0, n_iss = 1;
-      // Descriptors are built once; per MMA only the 14-bit start-address field (units of 16 B == staged
-      // rows) is advanced.  Every kernel parameter the loop needs is copied to a register first: reads of the
-      // parameter bank inside the loop (forced by the asm memory clobbers) cost tens of cycles each in a
-      // single-thread instruction stream and were the bottleneck of this role.
-      const int N = p.N, n_tiles = p.n_tiles, ntaps = p.ntaps, nchunks = p.nchunks, Wp = p.Wp;
-      const int a_stages = p.a_stages, w_stages = p.w_stages, acc_bufs = p.acc_bufs;
-      const bool w_resident = p.w_resident != 0, skip_mma = (p.debug & 4) != 0;
-      const int cl = p.cluster;
-      const uint32_t idesc = umma_idesc_bf16(128, N);
-      const uint64_t desc_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
-      const uint32_t a_lo0 = (smem_u32(As) >> 4) | (static_cast<uint32_t>(p.R) << 16);  // LBO = R*16 B
-      const uint32_t w_lo0 = (smem_u32(Ws) >> 4) | (static_cast<uint32_t>(N) << 16);    // LBO = N*16 B
-      const uint32_t a_stage_u = p.a_stage_bytes >> 4, w_slab_u = p.w_slab_bytes >> 4;
-      const uint32_t kstep_a = 2 * p.R, kstep_w = 2 * N;
-      const uint32_t acc_stride = n_tiles * N;
-      const int tap0 = (w_resident || ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
-      int a_it = 0, w_it = 0;
-      if (w_resident && my_groups > 0) {
-        if (iw == 0) {  // the resident filter is fetched once per CTA
-          const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
-          mbar_arrive_expect_tx(&bar_w_full[0], p.n_slabs * p.w_slab_bytes);
-          for (int sidx = 0; sidx < p.n_slabs; ++sidx)
-            bulk_g2s(Ws + sidx * p.w_slab_bytes, wg + static_cast<size_t>(sidx) * p.w_slab_bytes, p.w_slab_bytes, &bar_w_full[0]);
-        }
-        mbar_wait(&bar_w_full[0], 0);
-        tc_fence_after_sync();
+    // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic on the uniform
+    // datapath: inside a one-lane divergent region every tcgen05.mma operand needed its own R2UR move, and the tap
+    // loop went through an indirect branch); only the elected lane issues MMAs, commits and copies.  The tile count
+    // and the MMA order are compile-time constants of the loop body, chosen once per kernel.
+    const bool leader = elect_one();
+    const int N = p.N, ntaps = p.ntaps, nchunks = p.nchunks, Wp = p.Wp;
+    const int a_stages = p.a_stages, w_stages = p.w_stages, acc_bufs = p.acc_bufs;
+    const bool w_resident = p.w_resident != 0, skip_mma = (p.debug & 4) != 0;
+    const int cl = p.cluster;
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    const uint64_t desc_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
+    const uint32_t a_lo0 = (smem_u32(As) >> 4) | (static_cast<uint32_t>(p.R) << 16);  // LBO = R*16 B
+    const uint32_t w_lo0 = (smem_u32(Ws) >> 4) | (static_cast<uint32_t>(N) << 16);    // LBO = N*16 B
+    const uint32_t a_stage_u = p.a_stage_bytes >> 4, w_slab_u = p.w_slab_bytes >> 4;
+    const uint32_t kstep_a = 2 * p.R, kstep_w = 2 * N;
+    const uint32_t acc_stride = p.n_tiles * N;
+    const int tap0 = (w_resident || ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
+    if (w_resident && my_groups > 0) {
+      if (leader) {  // the resident filter is fetched once per CTA
+        const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
+        mbar_arrive_expect_tx(&bar_w_full[0], p.n_slabs * p.w_slab_bytes);
+        for (int sidx = 0; sidx < p.n_slabs; ++sidx)
+          bulk_g2s(Ws + sidx * p.w_slab_bytes, wg + static_cast<size_t>(sidx) * p.w_slab_bytes, p.w_slab_bytes, &bar_w_full[0]);
       }
+      mbar_wait(&bar_w_full[0], 0);
+      tc_fence_after_sync();
+    }
+    auto run = [&](auto nt_c, auto outer_c) {
+      constexpr int NT = decltype(nt_c)::value;
+      constexpr bool TILE_OUTER = decltype(outer_c)::value;
+      int a_it = 0, w_it = 0;
       for (int li = 0; li < my_groups; ++li) {
         const int buf = li % acc_bufs, useb = li / acc_bufs;
-        if (iw == 0) RD_TRACE(0, li, 0);
+        if (leader) RD_TRACE(0, li, 0);
         if (useb > 0) { mbar_wait(&bar_acc_empty[buf], (useb - 1) & 1); tc_fence_after_sync(); }
-        if (iw == 0) RD_TRACE(0, li, 1);
+        if (leader) RD_TRACE(0, li, 1);
         const uint32_t acc = tmem + buf * acc_stride;
         for (int chunk = 0; chunk < nchunks; ++chunk, ++a_it) {
           const int stage = a_it % a_stages;
           mbar_wait(&bar_a_full[stage], (a_it / a_stages) & 1);
           tc_fence_after_sync();
-          if (chunk == 0 && iw == 0) RD_TRACE(0, li, 2);
+          if (chunk == 0 && leader) RD_TRACE(0, li, 2);
           const uint32_t a_lo_stage = a_lo0 + stage * a_stage_u;
           // Streamed filters: every CTA walks the taps of a chunk in its own rotation, so that the 148 CTAs do
           // not all pull the same 16 KB slab out of the same L2 slices at the same moment.
@@ -275,49 +338,38 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               tc_fence_after_sync();
               w_lo = w_lo0 + ws * w_slab_u;
             }
-            const uint32_t a_lo = a_lo_stage + shift;
-            const uint32_t accum = (chunk | tcount) != 0;
-            if (!skip_mma) {
-              if (N <= 64) {
-                // narrow N: keep the tiles of one k-step together
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint64_t db = desc_hi | (w_lo + kk * kstep_w);
-                  const uint32_t a_k = a_lo + kk * kstep_a;
-#pragma unroll
-                  for (int tt = 0; tt < 4; ++tt) {
-                    const int tile = iw + tt * n_iss;
-                    if (tile < n_tiles) umma_bf16_ss(acc + tile * N, desc_hi | (a_k + tile * 128), db, idesc, accum | (kk != 0));
-                  }
-                }
-              } else {
-                // N >= 128: the four k-steps of a tile back to back on the same accumulator (65 vs 86 cycles per
-                // MMA on B200, tools/probe_umma2.cu)
-#pragma unroll
-                for (int tt = 0; tt < 4; ++tt) {
-                  const int tile = iw + tt * n_iss;
-                  if (tile < n_tiles) {
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                      umma_bf16_ss(acc + tile * N, desc_hi | (a_lo + tile * 128 + kk * kstep_a), desc_hi | (w_lo + kk * kstep_w), idesc,
-                                   accum | (kk != 0));
-                  }
-                }
+            if (leader) {
+              if (!skip_mma)
+                issue_tap<NT, TILE_OUTER>(acc, static_cast<uint32_t>(N), a_lo_stage + shift, w_lo, kstep_a, kstep_w, desc_hi, idesc,
+                                          (chunk | tcount) != 0);
+              if (!w_resident) {
+                if (cl > 1) umma_commit_multicast(&bar_w_empty[ws], cmask); else umma_commit(&bar_w_empty[ws]);
               }
             }
-            if (!w_resident) {
-              if (cl > 1) umma_commit_multicast(&bar_w_empty[ws], cmask); else umma_commit(&bar_w_empty[ws]);
-              ++w_it;
-            }
+            if (!w_resident) ++w_it;
             // next tap: (dy,dx) -> row shift dy*Wp + dx, wrapping around after the last tap
             if (++tap == ntaps) { tap = 0; col = 0; shift = 0; }
             else if (++col == 3) { col = 0; shift += Wp - 2; } else { shift += 1; }
           }
-          umma_commit(&bar_a_empty[stage]);  // operand stage reusable once these MMAs have read it
+          if (leader) umma_commit(&bar_a_empty[stage]);  // operand stage reusable once these MMAs have read it
         }
-        umma_commit(&bar_acc_full[buf]);
-        if (iw == 0) RD_TRACE(0, li, 3);
+        if (leader) {
+          umma_commit(&bar_acc_full[buf]);
+          RD_TRACE(0, li, 3);
+        }
       }
+    };
+    using std::integral_constant;
+    const int sel = (N <= 64 ? 0 : 4) + p.n_tiles - 1;  // narrow N: tiles of a k-step together; N >= 128: tile-outer
+    switch (sel) {
+      case 0: run(integral_constant<int, 1>{}, integral_constant<bool, false>{}); break;
+      case 1: run(integral_constant<int, 2>{}, integral_constant<bool, false>{}); break;
+      case 2: run(integral_constant<int, 3>{}, integral_constant<bool, false>{}); break;
+      case 3: run(integral_constant<int, 4>{}, integral_constant<bool, false>{}); break;
+      case 4: run(integral_constant<int, 1>{}, integral_constant<bool, true>{}); break;
+      case 5: run(integral_constant<int, 2>{}, integral_constant<bool, true>{}); break;
+      case 6: run(integral_constant<int, 3>{}, integral_constant<bool, true>{}); break;
+      default: run(integral_constant<int, 4>{}, integral_constant<bool, true>{}); break;
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -347,133 +399,84 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     // ================================================================ epilogue
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int et = q * 32 + lane;
-    const int cblocks = p.N / 32;
-    const int nblocks = p.n_tiles * cblocks;
-    const size_t out_gstride = static_cast<size_t>(p.S) * p.Ho * p.Wo * p.N;
-    constexpr int BTR = 8;  // (sample, channel) terms a thread carries in registers; the rest is loaded synchronously
-    float btv[BTR];
-    auto bt_value = [&](int g, int i) {
-      const int s = i / p.N, c = i - s * p.N;
-      float v = __ldg(p.bias + c);
-      if (p.tproj) {
-        int row = g * p.S + s;
-        if (p.tproj_wrap > 0 && row > p.tproj_wrap) row = p.tproj_wrap;  // shared unconditional-CFG row
-        v += __ldg(p.tproj + static_cast<size_t>(row) * p.tproj_stride + p.tproj_off + c);
-      }
-      return v * p.out_scale;
-    };
-    auto bt_load = [&](float (&v)[BTR], int g) {
-      const int n = min(p.S, p.B2 - g * p.S) * p.N;
-#pragma unroll
-      for (int k = 0; k < BTR; ++k) {
-        const int i = et + k * EPI_WARPS * 32;
-        if (i < n) v[k] = bt_value(g, i);
+    const int N = p.N, n_tiles = p.n_tiles, S = p.S;
+    const float oscale = p.out_scale;
+    const bool skip_ld = (p.debug & 16) != 0, skip_work = (p.debug & 2) != 0;
+    const size_t out_gstride = static_cast<size_t>(S) * p.Ho * p.Wo * N;
+    // (bias + Dense_0(SiLU(temb))) * out_scale for every (sample, channel) of group g, written straight into one
+    // half of the double-buffered table in shared memory (the other half is being read by the current group).
+    auto bt_fill = [&](float* dst, int g) {
+      const int n = min(S, p.B2 - g * S) * N;
+      for (int i = et; i < n; i += EPI_WARPS * 32) {
+        const int s = i / N, c = i - s * N;
+        float v = __ldg(p.bias + c);
+        if (p.tproj) {
+          int row = g * S + s;
+          if (p.tproj_wrap > 0 && row > p.tproj_wrap) row = p.tproj_wrap;  // shared unconditional-CFG row
+          v += __ldg(p.tproj + static_cast<size_t>(row) * p.tproj_stride + p.tproj_off + c);
+        }
+        dst[i] = v * oscale;
       }
     };
-    auto bt_store = [&](const float (&v)[BTR], float* dst, int g) {
-      const int n = min(p.S, p.B2 - g * p.S) * p.N;
-#pragma unroll
-      for (int k = 0; k < BTR; ++k) {
-        const int i = et + k * EPI_WARPS * 32;
-        if (i < n) dst[i] = v[k];
-      }
-      for (int i = et + BTR * EPI_WARPS * 32; i < n; i += EPI_WARPS * 32) dst[i] = bt_value(g, i);
-    };
+    if (my_groups > 0) bt_fill(s_bt, blockIdx.x);
     for (int li = 0; li < my_groups; ++li) {
       const int g = blockIdx.x + li * gridDim.x;
-      const int sample0 = g * p.S;
-      const int S_act = max(0, min(p.S, p.B2 - sample0));
+      const int S_act = max(0, min(S, p.B2 - g * S));
       const int buf = li % p.acc_bufs;
-      // per-(sample, channel) additive term (bias + Dense_0(SiLU(temb))) * out_scale, staged through shared memory.
-      // The values of the NEXT group are fetched into registers here and stored after this group's body, so the
-      // global-load latency hides behind the accumulator wait.
-      float* bt = s_bt + (li & 1) * p.S * p.N;
-      if (li == 0) {
-        bt_load(btv, g);
-        bt_store(btv, bt, g);
-      }
+      const float* bt = s_bt + (li & 1) * S * N;
       if (et == 0) RD_TRACE(1, li, 0);
-      epi_bar();
+      epi_bar();  // this group's table is complete; the other half is no longer read by anyone
       if (et == 0) RD_TRACE(1, li, 1);
-      const bool have_next = li + 1 < my_groups;
-      if (have_next) bt_load(btv, g + gridDim.x);
+      // next group's table: its global-load latency hides behind the accumulator wait below
+      if (li + 1 < my_groups) bt_fill(s_bt + ((li + 1) & 1) * S * N, g + gridDim.x);
       mbar_wait(&bar_acc_full[buf], (li / p.acc_bufs) & 1);
       tc_fence_after_sync();
       if (et == 0) RD_TRACE(1, li, 2);
-      const uint32_t acc = tmem + buf * p.n_tiles * p.N + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t acc = tmem + buf * n_tiles * N + (static_cast<uint32_t>(q * 32) << 16);
       __nv_bfloat16* og = p.out + static_cast<size_t>(g) * out_gstride;
       const __nv_bfloat16* rg = p.residual ? p.residual + static_cast<size_t>(g) * out_gstride : nullptr;
-      const int valid_limit = S_act * p.Ho * p.Wo * p.N;
-      const bool skip_ld = (p.debug & 16) != 0;
-      const int N = p.N;
-      const float oscale = p.out_scale;
-      uint4 res[4];
-      {  // residual prefetch for block 0
-        const int orow = t_orow[q * 32 + lane];
-        if (rg && orow >= 0 && orow < valid_limit) {
+      const int valid_limit = S_act * p.Ho * p.Wo * N;
+      // A thread owns one accumulator row per 128-row tile and walks it in blocks of 32 columns.  One warp per TMEM
+      // lane quarter runs this loop, so it is bound by dependent-instruction latency: per-row state is computed once
+      // per tile, nothing is divided, and the residual of the next block is requested before the current one is used.
+      for (int tile = 0; tile < n_tiles; ++tile) {
+        const int row = tile * 128 + et;
+        const int orow = t_orow[row];
+        const bool valid = orow >= 0 && orow < valid_limit && !skip_work;
+        const float* btr = bt + t_os[row] * N;
+        __nv_bfloat16* orow_ptr = og + orow;
+        const __nv_bfloat16* rrow_ptr = rg + orow;
+        uint4 res[4];
+        if (rg && valid) {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const u32x8 t = ld_global_256(rg + orow + 16 * j);
+            const u32x8 t = ld_global_256(rrow_ptr + 16 * j);
             res[2 * j] = make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]);
             res[2 * j + 1] = make_uint4(t.v[4], t.v[5], t.v[6], t.v[7]);
           }
         }
-      }
-      for (int blk = 0; blk < nblocks; ++blk) {
-        const int tile = blk / cblocks, c0 = (blk - tile * cblocks) * 32;
-        const int row = tile * 128 + q * 32 + lane;
-        const int orow = t_orow[row];
-        const bool valid = orow >= 0 && orow < valid_limit && !(p.debug & 2);
-        uint32_t v[32];
-        if (!skip_ld) tmem_ld32(acc + tile * N + c0, v);
-        uint4 cur[4];
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t v[32];
+          if (!skip_ld) tmem_ld32(acc + tile * N + c0, v);
+          uint4 cur[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = res[j];
-        if (rg && blk + 1 < nblocks) {  // prefetch the next block's residual while this one is processed
-          const int nt = (blk + 1) / cblocks, nc0 = (blk + 1 - nt * cblocks) * 32;
-          const int nor = t_orow[nt * 128 + q * 32 + lane];
-          if (nor >= 0 && nor < valid_limit) {
+          for (int j = 0; j < 4; ++j) cur[j] = res[j];
+          if (rg && valid && c0 + 32 < N) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const u32x8 t = ld_global_256(rg + nor + nc0 + 16 * j);
+              const u32x8 t = ld_global_256(rrow_ptr + c0 + 32 + 16 * j);
               res[2 * j] = make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]);
               res[2 * j + 1] = make_uint4(t.v[4], t.v[5], t.v[6], t.v[7]);
             }
           }
-        }
-        if (!skip_ld) tmem_ld_wait();
-        if (valid) {
-          const float* btr = bt + t_os[row] * N + c0;
-          uint4 outv[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b0 = *reinterpret_cast<const float4*>(btr + 8 * j), b1 = *reinterpret_cast<const float4*>(btr + 8 * j + 4);
-            float a[8] = {fmaf(__uint_as_float(v[8 * j]), oscale, b0.x), fmaf(__uint_as_float(v[8 * j + 1]), oscale, b0.y),
-                          fmaf(__uint_as_float(v[8 * j + 2]), oscale, b0.z), fmaf(__uint_as_float(v[8 * j + 3]), oscale, b0.w),
-                          fmaf(__uint_as_float(v[8 * j + 4]), oscale, b1.x), fmaf(__uint_as_float(v[8 * j + 5]), oscale, b1.y),
-                          fmaf(__uint_as_float(v[8 * j + 6]), oscale, b1.z), fmaf(__uint_as_float(v[8 * j + 7]), oscale, b1.w)};
-            if (rg) {
-              float r[8];
-              unpack8(cur[j], r);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a[e] = fmaf(r[e], oscale, a[e]);
-            }
-            outv[j] = pack8(a);
-          }
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            u32x8 t;
-            t.v[0] = outv[2 * j].x; t.v[1] = outv[2 * j].y; t.v[2] = outv[2 * j].z; t.v[3] = outv[2 * j].w;
-            t.v[4] = outv[2 * j + 1].x; t.v[5] = outv[2 * j + 1].y; t.v[6] = outv[2 * j + 1].z; t.v[7] = outv[2 * j + 1].w;
-            st_global_256(og + orow + c0 + 16 * j, t);
-          }
+          if (!skip_ld) tmem_ld_wait32(v);
+          if (valid) epi_finish_block(v, btr + c0, oscale, rg ? cur : nullptr, orow_ptr + c0, p.debug);
         }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
       if (et == 0) RD_TRACE(1, li, 3);
-      if (have_next) bt_store(btv, s_bt + ((li + 1) & 1) * p.S * p.N, g + gridDim.x);
     }
   } else {
     // ================================================================ transform (warps 2,3,8..15)
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         if (active) gn_coeffs(s, kc * 8, ca, cb);
         for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
           const int stage = a_it % p.a_stages;
-          if (a_it >= p.a_stages) mbar_wait(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
+          if (a_it >= p.a_stages) mbar_wait_relaxed(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
           if (xt == 0 && chunk == 0) RD_TRACE(2, li, 4);
           if (active && chunk == my_chunk) {
             uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes) + kcl * p.R;
@@ -708,7 +711,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const int items = S_act * P * 8;
         for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
           const int stage = a_it % p.a_stages;
-          if (a_it >= p.a_stages) mbar_wait(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
+          if (a_it >= p.a_stages) mbar_wait_relaxed(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
           uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes);
           const int which = (chunk * 64 < p.C[0]) ? 0 : 1;  // C[0] is a multiple of 64 whenever there are two sources
           const __nv_bfloat16* base = (which ? gb1 - p.C[0] : gb0) + chunk * 64;

@@ -52,6 +52,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait for roles with slack (operand transform, weight producer): back off between polls so that the polling
+// warps do not take issue slots from the warps on the critical path that share their scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 200) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if (++spins > (1u << 22)) { __trap(); }
+  }
+}
+
 // ---------------------------------------------------------------- proxies / fences
 // Make generic-proxy st.shared visible to the async proxy (tcgen05.mma / bulk copies read smem through it).
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -181,6 +191,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, with the destination registers of the load named as read-write operands: no use of `v` can be
+// scheduled above the wait (needed when another tcgen05.ld is issued between the wait and the uses).
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
+                 "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                 "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
 // 256-bit global accesses (sm_100+): a thread that owns 32 contiguous bytes moves them with one instruction,
 // halving the L1 wavefronts of row-per-thread epilogues compared with 2 x 128-bit.

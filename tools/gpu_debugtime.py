@@ -18,6 +18,6 @@ for _ in range(reps):
         eng.run_ops(i, 1); ev[i + 1].record()
     torch.cuda.synchronize()
     for i in range(eng.n_ops): per[i] += ev[i].elapsed_time(ev[i + 1]) / reps
-sel = ["down_blocks.0.Conv_0", "down_blocks.0", "down_attn.0.qkv", "down_attn.0", "down_blocks.3.Conv_0", "mid_block1.Conv_0", "up_blocks.3.Conv_0", "upsample.1", "up_blocks.6.Conv_0", "up_blocks.7.Conv_0", "up_blocks.6.NIN_0"]
+sel = ["down_blocks.0.Conv_0", "down_blocks.0", "down_blocks.3.Conv_0", "mid_block1.Conv_0", "up_blocks.3.Conv_0", "upsample.1", "up_blocks.6.Conv_0", "up_blocks.7.Conv_0", "up_blocks.6.NIN_0"]
 d = dict(zip(eng.op_names, per))
 print("DEBUG=%s conv total %.3f | " % (os.environ.get("RD_CONV_DEBUG", "0"), sum(t for t, n in zip(per, eng.op_names) if eng.op_kinds[n] == "conv")) + " ".join("%s=%.3f" % (k.replace("blocks.", "b").replace("Conv_0", "c0"), d[k]) for k in sel))

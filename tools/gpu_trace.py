@@ -26,3 +26,18 @@ for name in sys.argv[1:] or ["down_blocks.0.Conv_0"]:
             (li,) + tuple(r[0, li, :4]) + tuple(r[1, li, :4]) + tuple(r[2, li, :8])))
     last = r[r >= 0].max()
     print("total cycles", last)
+    # compact steady-state summary (groups 4..11)
+    gs = range(4, 12)
+    def avg(f): return sum(f(li) for li in gs) / len(gs)
+    print("SUMMARY %s debug=%s: period %.0f | MMA issue %.0f exec(accF - max(prev accF, aFull)) %.0f accE-wait %.0f | EPI accF->done %.0f wait-accF %.0f | XF load+rec %.0f stats %.0f aEmpty-wait %.0f norm+store %.0f" % (
+        name, os.environ.get("RD_CONV_DEBUG", "0"),
+        avg(lambda li: r[0, li + 1, 0] - r[0, li, 0]),
+        avg(lambda li: r[0, li, 3] - r[0, li, 2]),
+        avg(lambda li: r[1, li, 2] - max(r[1, li - 1, 2], r[0, li, 2])),
+        avg(lambda li: r[0, li, 1] - r[0, li, 0]),
+        avg(lambda li: r[1, li, 3] - r[1, li, 2]),
+        avg(lambda li: r[1, li, 2] - r[1, li, 1]),
+        avg(lambda li: r[2, li, 1] - r[2, li, 0]),
+        avg(lambda li: r[2, li, 3] - r[2, li, 1]),
+        avg(lambda li: r[2, li, 4] - r[2, li, 3]),
+        avg(lambda li: r[2, li, 5] - r[2, li, 4])))

@@ -32,16 +32,18 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(128) probe2(const __nv_bfloat16* __restrict__ Ag, const __nv_bfloat16* __restrict__ Bg,
+__global__ void __launch_bounds__(512) probe2(const __nv_bfloat16* __restrict__ Ag, const __nv_bfloat16* __restrict__ Bg,
                                                float* __restrict__ D, long long* __restrict__ cyc, int layout, int R, int N,
-                                               int shift, int ntiles, int reps, int order, int noise) {
+                                               int shift, int ntiles, int reps, int order, int noise, uint4* __restrict__ gscratch, int smem_off) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar, bar2;
   const int stage_bytes = ((8 * R * 16 + 127) / 128) * 128;
-  __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t tmem_slot_arr[2];
+  uint32_t& tmem_slot = tmem_slot_arr[0];
+  if (threadIdx.x == 0) tmem_slot_arr[1] = 0;
   const int a_bytes = 2 * stage_bytes;  // two operand stages (layout 0: [8][R][16 B] each)
-  unsigned char* As = smem;
-  unsigned char* Bs = smem + ((a_bytes + 1023) / 1024) * 1024;
+  unsigned char* As = smem + smem_off;
+  unsigned char* Bs = smem_off ? As + a_bytes : smem + ((a_bytes + 1023) / 1024) * 1024;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1000000); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -95,6 +97,11 @@ __global__ void __launch_bounds__(128) probe2(const __nv_bfloat16* __restrict__ 
             if (++col == 3) { col = 0; sh += 8; } else { sh += 1; }
           }
           if (order == 4) umma_commit(&bar2);
+          if (order == 7) {  // drain after every group: commit, wait for it, fence, then continue
+            umma_commit(&bar);
+            mbar_wait(&bar, rep & 1);
+            tc_fence_after_sync();
+          }
         } else if (order == 3) {
           int sh = 0, col = 0;
           for (int tap = 0; tap < 9; ++tap) {
@@ -117,12 +124,86 @@ __global__ void __launch_bounds__(128) probe2(const __nv_bfloat16* __restrict__ 
             }
         }
       }
-      umma_commit(&bar);
-      mbar_wait(&bar, 0);
+      if (order != 7) { umma_commit(&bar); mbar_wait(&bar, 0); }
       t1 = clock64();
       cyc[0] = t1 - t0;
+      *reinterpret_cast<volatile int*>(&tmem_slot + 1) = 1;
     }
     __syncwarp();
+  } else if (noise >= 700) {
+    // 700+k: a full epilogue on warps 4..7 next to the MMAs: tcgen05.ld of an idle TMEM region, 32 FFMA, bf16 packs and
+    // two scattered 256-bit stores per row into a large buffer (DRAM write traffic), k*100 blocks per warp.
+    // 800+k: the same without the tcgen05.ld.  900+k: without the stores.
+    if (warp >= 4) {
+      const int k = noise % 100;
+      const size_t wrap = (size_t)1 << (noise >= 750 && noise < 800 ? 26 : 22);  // uint4 units: 64 MB window (L2 resident) or 1 GB (DRAM) for 750..799
+      size_t pos = (static_cast<size_t>(blockIdx.x) * 128 + (tid - 128)) * 8;
+      uint32_t v[32];
+      for (int j = 0; j < 32; ++j) v[j] = tid + j;
+      const long long n0 = clock64();
+      for (int i = 0; i < k * 100; ++i) {
+        if (noise < 800 || noise >= 900) {
+          tmem_ld32(tmem + (((warp & 3) * 32) << 16) + 384 + (i & 3) * 32, v);
+          tmem_ld_wait32(v);
+        }
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaf(__uint_as_float(v[2 * j]), 0.7071f, 0.25f), b = fmaf(__uint_as_float(v[2 * j + 1]), 0.7071f, 0.5f);
+          __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          o[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (noise < 900) {
+          uint4* dst = gscratch + (pos & (wrap - 1));
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 2), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]) : "memory");
+          pos += static_cast<size_t>(gridDim.x) * 128 * 8;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[2 * j] ^= o[j];
+        }
+      }
+      if (v[4] == 0x12345u) D[2] = 1.f;
+      if (tid == 128) cyc[1] = (clock64() - n0) / (k * 100);
+    }
+  } else if (noise >= 500) {
+    // 500+: warps 4..15 sit in mbarrier try_wait (with the suspend hint) on a barrier that never completes, like the
+    // idle roles of the conv kernel, until the issuer raises a flag; 600+: the same with plain polling (no hint)
+    if (warp >= 4) {
+      volatile int* flag = reinterpret_cast<volatile int*>(&tmem_slot + 1);
+      while (*flag == 0) {
+        if (noise < 600) (void)mbar_try_wait(&bar2, 0);
+        else {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar2)), "r"(0) : "memory");
+        }
+      }
+    }
+  } else if (noise >= 200) {
+    // epilogue-like noise on warps 4..7 (warp 5 shares the issuer's scheduler):
+    //   200+k ALU only (FFMA + bf16 packs), 300+k scattered 256-bit global stores, 400+k ALU on warps 4,6,7 only
+    if (warp >= 4 && !(noise >= 400 && warp == 5)) {
+      const int k = noise % 100;
+      float a[16];
+      for (int j = 0; j < 16; ++j) a[j] = tid * 0.001f + j;
+      uint32_t pk[8];
+      for (int i = 0; i < k * 1000; ++i) {
+        if (noise < 300 || noise >= 400) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], 1.0001f, 0.5f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * j], a[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            a[2 * j] += __uint_as_float(pk[j] << 16) * 1e-9f;
+          }
+        } else {
+          uint4* dst = gscratch + (static_cast<size_t>(blockIdx.x) * 128 + (tid - 128)) * 8 + (i & 3) * 2;
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(i), "r"(i), "r"(i), "r"(i), "r"(i), "r"(i), "r"(i), "r"(i) : "memory");
+        }
+      }
+      if (a[3] == 0.12345f) D[2] = pk[1];
+    }
   } else if (noise >= 100) {
     // TMEM read traffic concurrent with the MMAs (epilogue-like): tcgen05.ld of columns 256..
     uint32_t acc = 0;
@@ -145,7 +226,7 @@ __global__ void __launch_bounds__(128) probe2(const __nv_bfloat16* __restrict__ 
   }
   __syncthreads();
   tc_fence_after_sync();
-  for (int tile = 0; tile < ntiles; ++tile)
+  for (int tile = 0; tile < ntiles && warp < 4; ++tile)
     for (int c0 = 0; c0 < N; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem + ((warp * 32) << 16) + tile * N + c0, v);
@@ -165,7 +246,7 @@ int main(int argc, char** argv) {
   int order = argc > 5 ? atoi(argv[5]) : 0;
   int noise = argc > 6 ? atoi(argv[6]) : 0;
   int grid = argc > 8 ? atoi(argv[8]) : 1;
-  int reps = 64;
+  int reps = (order == 9) ? 0 : 64;  // order 9: one warm-up group only (epilogue-noise timing without MMAs)
   int R = ntiles * 128 + 32 + (argc > 7 ? atoi(argv[7]) : 0);
   std::vector<int> A(R * 64), B(N * 64);
   for (int r = 0; r < R; ++r)
@@ -191,19 +272,20 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dA, Ap.size() * 2));
   CK(cudaMalloc(&dB, Bp.size() * 2));
   CK(cudaMalloc(&dD, ntiles * 128 * N * 4));
-  CK(cudaMalloc(&dC, 8));
+  CK(cudaMalloc(&dC, 16)); CK(cudaMemset(dC, 0, 16));
   CK(cudaMemcpy(dA, Ap.data(), Ap.size() * 2, cudaMemcpyHostToDevice));
   for (int t = 1; t < 9; ++t) for (int i = 0; i < N * 64; ++i) Bp[t * N * 64 + i] = Bp[i];
   CK(cudaMemcpy(dB, Bp.data(), Bp.size() * 2, cudaMemcpyHostToDevice));
   int smem = ((2 * (R * 128 + 128) + 1023) / 1024) * 1024 + 9 * N * 128 + 2048;
   CK(cudaFuncSetAttribute(probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe2<<<grid, 128, smem>>>(dA, dB, dD, dC, layout, R, N, shift, ntiles, reps, order, noise);
+  uint4* dS; CK(cudaMalloc(&dS, ((size_t)1 << 26) * 16 + (size_t)grid * 128 * 8 * 16));
+  probe2<<<grid, (noise >= 500 && noise < 700) ? 512 : (noise >= 200 ? 256 : 128), smem>>>(dA, dB, dD, dC, layout, R, N, shift, ntiles, reps, order, noise, dS, argc > 10 ? atoi(argv[10]) : 0);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   std::vector<float> D(ntiles * 128 * N);
-  long long cyc = 0;
+  long long cyc = 0, cyc_noise = 0;
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&cyc_noise, dC + 1, 8, cudaMemcpyDeviceToHost));
   int bad = 0;
   for (int m = 0; m < ntiles * 128; ++m)
     for (int n = 0; n < N; ++n) {
@@ -214,7 +296,7 @@ int main(int argc, char** argv) {
         ++bad;
       }
     }
-  printf("PROBE2 rnd=%d layout=%d N=%d shift=%d tiles=%d order=%d noise=%d grid=%d mismatches=%d cycles/MMA=%.1f\n", rnd, layout, N, shift, ntiles, order, noise, grid, bad,
-         (double)cyc / (reps * ntiles * 4 * (order >= 3 ? 9 : 1)));
+  printf("PROBE2 off=%d rnd=%d layout=%d N=%d shift=%d tiles=%d order=%d noise=%d grid=%d mismatches=%d cycles/MMA=%.1f noise_cycles/iter=%lld\n", argc > 10 ? atoi(argv[10]) : 0, rnd, layout, N, shift, ntiles, order, noise, grid, bad,
+         (double)cyc / (reps * ntiles * 4 * (order >= 3 ? 9 : 1)), cyc_noise);
   return bad ? 1 : 0;
 }
