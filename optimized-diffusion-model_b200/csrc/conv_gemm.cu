@@ -181,32 +181,57 @@ __device__ __forceinline__ void issue_tap(uint32_t acc, uint32_t N, uint32_t a_l
 
 // Epilogue body for one block (32 accumulator columns of the row this thread owns): scale, add the staged
 // (bias + temb) row, optionally add the residual, convert to bf16 and store 64 contiguous bytes.
+template <bool RES>
 __device__ __forceinline__ void epi_finish_block(const uint32_t (&v)[32], const float* __restrict__ btr, float oscale,
-                                                 const uint4* resv, __nv_bfloat16* dst, int dbg = 0) {
-  uint4 outv[4];
+                                                 const u32x8 (&resv)[2], __nv_bfloat16* dst) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float4 b0, b1;
-    if (dbg & 128) { b0 = make_float4(oscale, oscale, oscale, oscale); b1 = b0; }
-    else { b0 = *reinterpret_cast<const float4*>(btr + 8 * j); b1 = *reinterpret_cast<const float4*>(btr + 8 * j + 4); }
-    float a[8] = {fmaf(__uint_as_float(v[8 * j]), oscale, b0.x), fmaf(__uint_as_float(v[8 * j + 1]), oscale, b0.y),
-                  fmaf(__uint_as_float(v[8 * j + 2]), oscale, b0.z), fmaf(__uint_as_float(v[8 * j + 3]), oscale, b0.w),
-                  fmaf(__uint_as_float(v[8 * j + 4]), oscale, b1.x), fmaf(__uint_as_float(v[8 * j + 5]), oscale, b1.y),
-                  fmaf(__uint_as_float(v[8 * j + 6]), oscale, b1.z), fmaf(__uint_as_float(v[8 * j + 7]), oscale, b1.w)};
-    if (resv) {
-      float r[8];
-      unpack8(resv[j], r);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = fmaf(r[e], oscale, a[e]);
-    }
-    outv[j] = pack8(a);
-  }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
+  for (int h = 0; h < 2; ++h) {
     u32x8 t;
-    t.v[0] = outv[2 * j].x; t.v[1] = outv[2 * j].y; t.v[2] = outv[2 * j].z; t.v[3] = outv[2 * j].w;
-    t.v[4] = outv[2 * j + 1].x; t.v[5] = outv[2 * j + 1].y; t.v[6] = outv[2 * j + 1].z; t.v[7] = outv[2 * j + 1].w;
-    if (!(dbg & 64) || t.v[0] == 0x12345678u) st_global_256(dst + 16 * j, t);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int o = 16 * h + 8 * j;
+      const float4 b0 = *reinterpret_cast<const float4*>(btr + o), b1 = *reinterpret_cast<const float4*>(btr + o + 4);
+      float a[8] = {fmaf(__uint_as_float(v[o]), oscale, b0.x),     fmaf(__uint_as_float(v[o + 1]), oscale, b0.y),
+                    fmaf(__uint_as_float(v[o + 2]), oscale, b0.z), fmaf(__uint_as_float(v[o + 3]), oscale, b0.w),
+                    fmaf(__uint_as_float(v[o + 4]), oscale, b1.x), fmaf(__uint_as_float(v[o + 5]), oscale, b1.y),
+                    fmaf(__uint_as_float(v[o + 6]), oscale, b1.z), fmaf(__uint_as_float(v[o + 7]), oscale, b1.w)};
+      if (RES) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t w = resv[h].v[4 * j + e];
+          a[2 * e] = fmaf(__uint_as_float(w << 16), oscale, a[2 * e]);
+          a[2 * e + 1] = fmaf(__uint_as_float(w & 0xffff0000u), oscale, a[2 * e + 1]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 hh = __floats2bfloat162_rn(a[2 * e], a[2 * e + 1]);
+        t.v[4 * j + e] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+    }
+    st_global_256(dst + 16 * h, t);
+  }
+}
+
+// One accumulator row of one 128-row tile, walked in blocks of 32 columns.  With a residual, the 64 bytes of the next
+// block are requested before the current block is converted (two register sets, no copies).
+template <bool RES>
+__device__ __forceinline__ void epi_row(uint32_t tacc, int N, const float* __restrict__ btr, float oscale,
+                                        const __nv_bfloat16* __restrict__ rrow, __nv_bfloat16* orow, bool valid, bool skip_ld) {
+  u32x8 ra[2], rb[2];
+  if (RES && valid) { ra[0] = ld_global_256(rrow); ra[1] = ld_global_256(rrow + 16); }
+  for (int c0 = 0; c0 < N; c0 += 64) {
+    uint32_t v[32];
+    if (!skip_ld) tmem_ld32(tacc + c0, v);
+    if (RES && valid && c0 + 32 < N) { rb[0] = ld_global_256(rrow + c0 + 32); rb[1] = ld_global_256(rrow + c0 + 48); }
+    if (!skip_ld) tmem_ld_wait32(v);
+    if (valid) epi_finish_block<RES>(v, btr + c0, oscale, ra, orow + c0);
+    if (c0 + 32 < N) {
+      if (!skip_ld) tmem_ld32(tacc + c0 + 32, v);
+      if (RES && valid && c0 + 64 < N) { ra[0] = ld_global_256(rrow + c0 + 64); ra[1] = ld_global_256(rrow + c0 + 80); }
+      if (!skip_ld) tmem_ld_wait32(v);
+      if (valid) epi_finish_block<RES>(v, btr + c0 + 32, oscale, rb, orow + c0 + 32);
+    }
   }
 }
 
@@ -444,34 +469,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const int orow = t_orow[row];
         const bool valid = orow >= 0 && orow < valid_limit && !skip_work;
         const float* btr = bt + t_os[row] * N;
-        __nv_bfloat16* orow_ptr = og + orow;
-        const __nv_bfloat16* rrow_ptr = rg + orow;
-        uint4 res[4];
-        if (rg && valid) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const u32x8 t = ld_global_256(rrow_ptr + 16 * j);
-            res[2 * j] = make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]);
-            res[2 * j + 1] = make_uint4(t.v[4], t.v[5], t.v[6], t.v[7]);
-          }
-        }
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t v[32];
-          if (!skip_ld) tmem_ld32(acc + tile * N + c0, v);
-          uint4 cur[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cur[j] = res[j];
-          if (rg && valid && c0 + 32 < N) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const u32x8 t = ld_global_256(rrow_ptr + c0 + 32 + 16 * j);
-              res[2 * j] = make_uint4(t.v[0], t.v[1], t.v[2], t.v[3]);
-              res[2 * j + 1] = make_uint4(t.v[4], t.v[5], t.v[6], t.v[7]);
-            }
-          }
-          if (!skip_ld) tmem_ld_wait32(v);
-          if (valid) epi_finish_block(v, btr + c0, oscale, rg ? cur : nullptr, orow_ptr + c0, p.debug);
-        }
+        if (rg) epi_row<true>(acc + tile * N, N, btr, oscale, rg + orow, og + orow, valid, skip_ld);
+        else epi_row<false>(acc + tile * N, N, btr, oscale, nullptr, og + orow, valid, skip_ld);
       }
       tc_fence_before_sync();
       __syncwarp();
