@@ -155,6 +155,30 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _latest_traffic_profile():
+    """profiles/*_conv_traffic.json is written by tools/summarise_ncu.py from an `ncu --metrics dram__bytes_*` capture
+    of the conv launches of this same workload (tools/run_gpu_round.sh); the newest round's file is used."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_conv_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            return json.load(f), os.path.relpath(files[-1], os.path.dirname(os.path.abspath(__file__)))
+    except Exception:
+        return None, None
+
+
+def conv_traffic_bytes():
+    js, _ = _latest_traffic_profile()
+    return None if js is None else js.get("dram_bytes_per_launch")
+
+
+def conv_traffic_source():
+    js, path = _latest_traffic_profile()
+    return None if js is None else "%s (ncu dram__bytes_read+write per conv launch, B=8192)" % path
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -274,7 +298,8 @@ def main():
         n_conv = sum(1 for n in eng.op_names if eng.op_kinds[n] == "conv")
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (all %d launches of one guided-score evaluation)" % n_conv,
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-                "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                "traffic": conv_traffic_bytes(), "traffic_source": conv_traffic_source(),
+                "peak_source": pk["source"] + " (sustained)",
                 "avg_launch_ms": conv_ms / n_conv, "share_of_forward": conv_ms / fwd_ms,
                 "algorithmic_flop_per_launch_avg": conv_flop / n_conv,
                 "sampler_frac": value / world * FLOP_PER_SAMPLE / (pk["bf16_tflops"] * 1e12)}

@@ -13,4 +13,8 @@ echo "ncu list rc=$?"
 timeout 200 python tools/prof_target.py > gpurun_out/prof_plain2.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 20 -c 4 -o gpurun_out/prof_conv python tools/prof_target.py > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+# DRAM bytes of every conv launch of two forwards (bench.py's roofline.traffic comes from this capture)
+timeout 200 python tools/prof_target.py > gpurun_out/prof_plain3.log 2>&1 && \
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_gemm -c 96 --csv --log-file gpurun_out/conv_traffic.csv python tools/prof_target.py > gpurun_out/ncu_traffic.log 2>&1
+echo "ncu traffic rc=$?"
 fi

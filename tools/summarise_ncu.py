@@ -36,4 +36,28 @@ if os.path.exists(rep):
         for i, h in enumerate(hdr):
             if keep.search(h) and not h.endswith("_not_issued"):
                 f.write("%-78s %-16s %s\n" % (h, units[i], " ; ".join(row[i][:28] for row in rows)))
+traffic = os.path.join(ROOT, "gpurun_out", "conv_traffic.csv")
+if os.path.exists(traffic):
+    import json
+    lines = [l for l in open(traffic) if not l.startswith("==")]
+    per = collections.defaultdict(dict)
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        if row["Metric Name"].startswith("dram__bytes"):
+            v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+        else:
+            v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(u, 1.0)
+        per[row["ID"]][row["Metric Name"]] = v
+    n = len(per)
+    rd = sum(d.get("dram__bytes_read.sum", 0.0) for d in per.values())
+    wr = sum(d.get("dram__bytes_write.sum", 0.0) for d in per.values())
+    us = sum(d.get("gpu__time_duration.sum", 0.0) for d in per.values())
+    js = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_gemm -c 96 python tools/prof_target.py",
+          "note": "per-launch averages over the conv_gemm launches of two guided forwards at 2B=16384; outputs mostly stay in the 126 MB L2 for the next layer, so writes are far below the algorithmic bytes",
+          "launches": n, "dram_read_bytes_per_launch": rd / max(n, 1), "dram_write_bytes_per_launch": wr / max(n, 1),
+          "dram_bytes_per_launch": (rd + wr) / max(n, 1), "ncu_us_per_launch": us / max(n, 1)}
+    with open(os.path.join(out, f"{tag}_conv_traffic.json"), "w") as f:
+        json.dump(js, f, indent=1)
+        f.write("\n")
 print("written to", out)
