@@ -177,90 +177,150 @@ int inconv_launch(const rd_op_inconv& op, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// out head: one CTA per guided sample; with CFG the conditional and unconditional copies are processed
-// concurrently by the two 128-thread halves of the CTA and combined at the end.
-constexpr int OH_THREADS = 128;  // per half
+// out head: out_norm + SiLU + 3x3 out_conv (C -> C_img) + CFG combine, one CTA per guided sample.
+// A warp owns whole pixels and a lane two channels of every 64-channel slab: pass 1 accumulates the GroupNorm sums,
+// pass 2 re-reads the same bf16 pairs (L1/L2 hits), normalises, applies SiLU and forms
+// the nine per-tap dot products q[px][tap] = sum_c w[tap][c] * act[px][c] (a vector warp reduction), and the conv
+// output is the 9-term gather y[px] = bias + sum_tap q[px + tap][tap].  Nothing is staged as fp32 in shared memory.  With CFG, warps 0-3 take the conditional copy and warps 4-7 the
+// unconditional one; the combine is the reference's (1+w)*cond - w*uncond in fp32.
+constexpr int OH_WARPS = 4;        // per copy
 
-__global__ void __launch_bounds__(2 * OH_THREADS) out_head_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ gamma,
-                                                                  const float* __restrict__ beta, const float* __restrict__ w,
-                                                                  const float* __restrict__ bias, const float* __restrict__ cfg_w,
-                                                                  float cfg_w_scalar, float* __restrict__ score, int B, int C,
-                                                                  int Cimg, int H, int W, int groups, int cfg, float eps) {
-  extern __shared__ __align__(16) float sm[];
-  const int P = H * W;
-  const int LD = C + 4;                // row stride: 16-B aligned, rows 4 banks apart -> conflict-free float4 reads
-  const int npass = cfg ? 2 : 1;
-  float* act_all = sm;                             // [2][P][LD]   (16-B aligned: LD % 4 == 0)
-  float* sw = act_all + 2 * P * LD;                // [Cimg][9][C] (tap-major; C % 4 == 0 keeps float4 alignment)
-  float* gsum_all = sw + Cimg * C * 9;             // [2][groups][2]
-  float* res = gsum_all + 2 * groups * 2;          // [2][Cimg][P]
-  const int tid = threadIdx.x & (OH_THREADS - 1), pass = threadIdx.x / OH_THREADS;
-  const int b = blockIdx.x;
-  const int cpg = C / groups;
-  float* act = act_all + pass * P * LD;
-  float* gsum = gsum_all + pass * groups * 2;
-  for (int i = threadIdx.x; i < Cimg * C * 9; i += blockDim.x) {
-    const int co = i / (C * 9), r = i - co * C * 9, c = r / 9, t = r - c * 9;
-    sw[(co * 9 + t) * C + c] = w[i];
-  }
-  const __nv_bfloat16* hb = h + static_cast<size_t>(b + pass * B) * P * C;
-  // load (coalesced 4-byte reads)
-  for (int i = tid; i < P * C / 2; i += OH_THREADS) {
-    const float2 f = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(hb)[i]);
-    const int px = (2 * i) / C, c = (2 * i) % C;
-    act[px * LD + c] = f.x;
-    act[px * LD + c + 1] = f.y;
-  }
-  __syncthreads();
-  for (int g = tid >> 5; g < groups; g += OH_THREADS / 32) {  // one warp per group
-    float sacc = 0.0f, q = 0.0f;
-    for (int i = tid & 31; i < P * cpg; i += 32) {
-      const float v = act[(i / cpg) * LD + g * cpg + (i % cpg)];
-      sacc += v; q += v * v;
-    }
+// Sum each of the 8 values of v[] over the 32 lanes with 9 shuffles (recursive halving): on return lane l holds the
+// total of value ((l >> 2) & 7) in v[0].
+__device__ __forceinline__ void warp_reduce8(float (&v)[8], int lane) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { sacc += __shfl_xor_sync(0xffffffffu, sacc, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if ((tid & 31) == 0) {
-      const float mean = sacc / static_cast<float>(P * cpg);
-      const float var = fmaxf(q / static_cast<float>(P * cpg) - mean * mean, 0.0f);
-      gsum[2 * g] = mean;
-      gsum[2 * g + 1] = 1.0f / sqrtf(var + eps);
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < P * C; i += OH_THREADS) {
-    const int px = i / C, c = i % C, g = c / cpg;
-    const float v = (act[px * LD + c] - gsum[2 * g]) * gsum[2 * g + 1] * gamma[c] + beta[c];
-    act[px * LD + c] = silu_acc(v);
-  }
-  __syncthreads();
-  for (int i = tid; i < Cimg * P; i += OH_THREADS) {
-    const int co = i / P, px = i % P, y = px / W, x = px % W;
-    float acc = bias[co];
-    for (int dy = 0; dy < 3; ++dy) {
-      const int yy = y + dy - 1;
-      if (yy < 0 || yy >= H) continue;
-      for (int dx = 0; dx < 3; ++dx) {
-        const int xx = x + dx - 1;
-        if (xx < 0 || xx >= W) continue;
-        const float4* a = reinterpret_cast<const float4*>(act + (yy * W + xx) * LD);
-        const float4* ww = reinterpret_cast<const float4*>(sw + (co * 9 + dy * 3 + dx) * C);
-        float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
-        for (int c4 = 0; c4 < C / 4; ++c4) {
-          const float4 av = a[c4], wv = ww[c4];
-          p0 = fmaf(av.x, wv.x, p0); p1 = fmaf(av.y, wv.y, p1); p2 = fmaf(av.z, wv.z, p2); p3 = fmaf(av.w, wv.w, p3);
-        }
-        acc += (p0 + p1) + (p2 + p3);
+  for (int step = 0; step < 3; ++step) {
+    const int half = 4 >> step;           // values kept after this step
+    const int mask = 16 >> step;          // partner distance
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < half) {
+        const float send = upper ? v[i] : v[i + half];
+        const float keep = upper ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
       }
     }
-    res[(pass * Cimg + co) * P + px] = acc;
   }
-  __syncthreads();
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__global__ void __launch_bounds__(2 * OH_WARPS * 32, 3) out_head_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, const float* __restrict__ cfg_w,
+                                                                     float cfg_w_scalar, float* __restrict__ score, int B, int C,
+                                                                     int Cimg, int H, int W, int groups, int cfg, float eps) {
+  extern __shared__ __align__(16) float sm[];
+  const int P = H * W;
+  const int npass = cfg ? 2 : 1;
+  float* q_all = sm;                                   // [2][Cimg][P][9]  per-tap dot products
+  float* csum = q_all + 2 * Cimg * P * 9;              // [2][OH_WARPS][C][2] per-warp channel sums
+  float* gstat = csum + 2 * OH_WARPS * C * 2;          // [2][groups][2] mean, rstd
+  const int warp_all = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pass = warp_all / OH_WARPS, wq = warp_all % OH_WARPS;
+  const int b = blockIdx.x;
+  const int cpg = C / groups;
+  const int nslab = C / 64;
+  const int ppw = (P + OH_WARPS - 1) / OH_WARPS;       // pixels per warp
+  const int px0 = wq * ppw;
+  const __nv_bfloat16* hb = h + static_cast<size_t>(b + pass * B) * P * C;
+  float* qh = q_all + pass * Cimg * P * 9;
+
+  for (int slab = 0; slab < nslab; ++slab) {
+    const int c = slab * 64 + 2 * lane;
+    // ---- pass 1: this lane's two channels of this warp's pixels -> registers, channel sums
+    float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+#pragma unroll 6
+    for (int i = 0; i < ppw; ++i) {
+      const int px = px0 + i;
+      if (px < P) {
+        const uint32_t xv = __ldg(reinterpret_cast<const uint32_t*>(hb + static_cast<size_t>(px) * C + c));
+        const float x0 = __uint_as_float(xv << 16), x1 = __uint_as_float(xv & 0xffff0000u);
+        s0 += x0; q0 = fmaf(x0, x0, q0);
+        s1 += x1; q1 = fmaf(x1, x1, q1);
+      }
+    }
+    float* cs = csum + ((pass * OH_WARPS + wq) * C + c) * 2;
+    cs[0] = s0; cs[1] = q0; cs[2] = s1; cs[3] = q1;
+    __syncthreads();
+    // group statistics of this slab's groups (fixed summation order: warps, then channels)
+    for (int g = threadIdx.x; g < 2 * (64 / cpg); g += blockDim.x) {
+      const int ps = g / (64 / cpg), gl = g % (64 / cpg);
+      if (ps < npass) {
+        float sa = 0.0f, sq = 0.0f;
+        for (int wv = 0; wv < OH_WARPS; ++wv)
+          for (int cc = 0; cc < cpg; ++cc) {
+            const float* src = csum + ((ps * OH_WARPS + wv) * C + slab * 64 + gl * cpg + cc) * 2;
+            sa += src[0]; sq += src[1];
+          }
+        const float inv = 1.0f / static_cast<float>(P * cpg);
+        const float mean = sa * inv;
+        const float var = fmaxf(sq * inv - mean * mean, 0.0f);
+        gstat[(ps * groups + slab * (64 / cpg) + gl) * 2] = mean;
+        gstat[(ps * groups + slab * (64 / cpg) + gl) * 2 + 1] = 1.0f / sqrtf(var + eps);
+      }
+    }
+    __syncthreads();
+    // ---- pass 2: normalise + SiLU from registers, nine per-tap dot products per pixel and output channel
+    const float* gs0 = gstat + (pass * groups + c / cpg) * 2;
+    const float* gs1 = gstat + (pass * groups + (c + 1) / cpg) * 2;
+    const float a0 = gs0[1] * gamma[c], b0 = fmaf(-gs0[0], a0, beta[c]);
+    const float a1 = gs1[1] * gamma[c + 1], b1 = fmaf(-gs1[0], a1, beta[c + 1]);
+    for (int co = 0; co < Cimg; ++co) {
+      float w0[9], w1[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        w0[t] = w[(static_cast<size_t>(co) * C + c) * 9 + t];
+        w1[t] = w[(static_cast<size_t>(co) * C + c + 1) * 9 + t];
+      }
+#pragma unroll 2
+      for (int i = 0; i < ppw; ++i) {
+        const int px = px0 + i;
+        if (px < P) {  // warp-uniform; the second read of the row hits L1/L2
+          const uint32_t xv = __ldg(reinterpret_cast<const uint32_t*>(hb + static_cast<size_t>(px) * C + c));
+          const float y0 = fmaf(__uint_as_float(xv << 16), a0, b0), y1 = fmaf(__uint_as_float(xv & 0xffff0000u), a1, b1);
+          const float act0 = silu_acc(y0), act1 = silu_acc(y1);
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = fmaf(act0, w0[t], act1 * w1[t]);
+          float v8 = fmaf(act0, w0[8], act1 * w1[8]);
+          warp_reduce8(v, lane);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(0xffffffffu, v8, o);
+          float* dst = qh + (co * P + px) * 9;
+          if ((lane & 3) == 0) {
+            const int t = (lane >> 2) & 7;
+            if (slab == 0) dst[t] = v[0]; else dst[t] += v[0];
+          }
+          if (lane == 1) { if (slab == 0) dst[8] = v8; else dst[8] += v8; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- 9-term gather per output pixel, CFG combine, NCHW fp32 store
   for (int i = threadIdx.x; i < Cimg * P; i += blockDim.x) {
-    float v = res[i];
+    const int co = i / P, px = i % P, y = px / W, x = px % W;
+    float r[2] = {0.0f, 0.0f};
+    for (int ps = 0; ps < npass; ++ps) {
+      float acc = bias[co];
+      const float* qq = q_all + (ps * Cimg + co) * P * 9;
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y + dy - 1;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = 0; dx < 3; ++dx) {
+          const int xx = x + dx - 1;
+          if (xx < 0 || xx >= W) continue;
+          acc += qq[(yy * W + xx) * 9 + dy * 3 + dx];
+        }
+      }
+      r[ps] = acc;
+    }
+    float v = r[0];
     if (npass == 2) {
       const float wv = cfg_w ? cfg_w[b] : cfg_w_scalar;
-      v = __fsub_rn(__fmul_rn(__fadd_rn(1.0f, wv), res[i]), __fmul_rn(wv, res[Cimg * P + i]));
+      v = __fsub_rn(__fmul_rn(__fadd_rn(1.0f, wv), r[0]), __fmul_rn(wv, r[1]));
     }
     score[static_cast<size_t>(b) * Cimg * P + i] = v;  // NCHW [B, Cimg, H, W]
   }
@@ -268,18 +328,13 @@ __global__ void __launch_bounds__(2 * OH_THREADS) out_head_kernel(const __nv_bfl
 
 int outhead_launch(const rd_op_outhead& op, cudaStream_t st) {
   RD_REQUIRE(op.h && op.gamma && op.beta && op.w && op.bias && op.score, "out_head: null pointer");
-  RD_REQUIRE(op.groups > 0 && op.C % op.groups == 0 && op.C % 4 == 0, "out_head: bad GroupNorm geometry");
+  RD_REQUIRE(op.groups > 0 && op.C % op.groups == 0 && op.C % 64 == 0, "out_head: C must be a multiple of 64 and of the group count");
+  RD_REQUIRE(64 % (op.C / op.groups) == 0, "out_head: channels per group must divide 64");
   RD_REQUIRE(op.cfg ? (op.B2 == 2 * op.B) : (op.B2 == op.B), "out_head: B2 must be 2B with cfg, B otherwise");
   const int P = op.H * op.W;
-  const int smem = (2 * P * (op.C + 4) + op.C_img * op.C * 9 + 2 * op.groups * 2 + 2 * op.C_img * P) * 4;
-  static int configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    RD_REQUIRE(smem <= 227 * 1024, "out_head: image too large for shared memory");
-    cudaError_t e = cudaFuncSetAttribute(out_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(static_cast<int>(e), "out_head: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
-  out_head_kernel<<<op.B, (op.cfg ? 2 : 1) * OH_THREADS, smem, st>>>(static_cast<const __nv_bfloat16*>(op.h), op.gamma, op.beta, op.w, op.bias,
+  const int smem = (2 * op.C_img * P * 9 + 2 * OH_WARPS * op.C * 2 + 2 * op.groups * 2) * 4;
+  RD_REQUIRE(smem <= 48 * 1024, "out_head: image too large for shared memory");
+  out_head_kernel<<<op.B, (op.cfg ? 2 : 1) * OH_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(op.h), op.gamma, op.beta, op.w, op.bias,
                                                   op.cfg_w, op.cfg_w_scalar, op.score, op.B, op.C, op.C_img, op.H, op.W,
                                                   op.groups, op.cfg, op.eps);
   return check_launch("out_head_kernel");
