@@ -164,8 +164,10 @@ namespace rd {
 
 constexpr int AB_LD = 72;  // bf16 row stride (144 B): conflict-free 32-bit fragment loads and ldmatrix rows
 
+constexpr int AB_G = 2;  // samples in flight per CTA: independent teams of T16 warps that share the weights in smem
+
 template <int T16>
-__global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_block_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                               const __nv_bfloat16* __restrict__ wqkv_t,   // [192][AB_LD]
                                                               const __nv_bfloat16* __restrict__ wproj_t,  // [64][AB_LD]
                                                               const float* __restrict__ bqkv, const float* __restrict__ bproj,
@@ -176,45 +178,52 @@ __global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat1
   extern __shared__ __align__(16) unsigned char smraw[];
   __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(smraw);  // [3C][AB_LD]
   __nv_bfloat16* Wp = Wq + 3 * C * AB_LD;                       // [C][AB_LD]
-  // two per-sample buffers, each used twice: raw rows -> (dead after normalisation) -> values;
-  // normalised rows -> (dead once every warp holds its A fragments) -> keys.  62 KB per CTA = 3 CTAs per SM.
-  __nv_bfloat16* Xr = Wp + C * AB_LD;                           // raw input rows   [TP][AB_LD]
+  // Each team (T16 warps, one sample at a time) owns two buffers, each used twice: raw rows -> (dead after
+  // normalisation) -> values; normalised rows -> (dead once every warp holds its A fragments) -> keys.  The weights
+  // are shared by the AB_G teams: 87 KB per CTA = 2 CTAs per SM = 4 samples in flight per SM (3 with one team per CTA).
+  const int team = threadIdx.x / (32 * T16);
+  const int tid = threadIdx.x - team * (32 * T16), warp = tid >> 5, lane = tid & 31;
+  constexpr int nthr = 32 * T16;
+  __nv_bfloat16* Xr = Wp + C * AB_LD + team * 2 * TP * AB_LD;   // raw input rows   [TP][AB_LD]
   __nv_bfloat16* Vs = Xr;                                       // values (aliases Xr)
   __nv_bfloat16* Xn = Xr + TP * AB_LD;                          // normalised rows  [TP][AB_LD]
   __nv_bfloat16* Ks = Xn;                                       // keys (aliases Xn)
-  float* s_par = reinterpret_cast<float*>(Xn + TP * AB_LD);     // bqkv[3C], bproj[C], gamma[C], beta[C], chsum[2C], gstat[2*groups]
+  float* s_par = reinterpret_cast<float*>(Wp + C * AB_LD + AB_G * 2 * TP * AB_LD);  // bqkv[3C], bproj[C], gamma[C], beta[C], per team: chsum[2C], gstat[2*groups]
   float* s_bq = s_par;
   float* s_bp = s_bq + 3 * C;
   float* s_ga = s_bp + C;
   float* s_be = s_ga + C;
-  float* s_cs = s_be + C;
+  float* s_cs = s_be + C + team * (2 * C + 2 * groups);
   float* s_gs = s_cs + 2 * C;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nthr = blockDim.x;
   const int g = lane >> 2, q4 = lane & 3;
   const int cpg = C / groups;
+  auto team_sync = [&]() {  // literal barrier ids keep the CTA's barrier allocation at 3 instead of all 16
+    if (team == 0) asm volatile("bar.sync 1, %0;" ::"n"(nthr) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(nthr) : "memory");
+  };
+  static_assert(AB_G == 2, "team_sync names two barriers");
 
-  for (int i = tid; i < 3 * C * AB_LD / 8; i += nthr) reinterpret_cast<uint4*>(Wq)[i] = reinterpret_cast<const uint4*>(wqkv_t)[i];
-  for (int i = tid; i < C * AB_LD / 8; i += nthr) reinterpret_cast<uint4*>(Wp)[i] = reinterpret_cast<const uint4*>(wproj_t)[i];
-  for (int i = tid; i < 3 * C; i += nthr) s_bq[i] = bqkv[i];
-  for (int i = tid; i < C; i += nthr) { s_bp[i] = bproj[i]; s_ga[i] = gamma[i]; s_be[i] = beta[i]; }
+  for (int i = threadIdx.x; i < 3 * C * AB_LD / 8; i += blockDim.x) reinterpret_cast<uint4*>(Wq)[i] = reinterpret_cast<const uint4*>(wqkv_t)[i];
+  for (int i = threadIdx.x; i < C * AB_LD / 8; i += blockDim.x) reinterpret_cast<uint4*>(Wp)[i] = reinterpret_cast<const uint4*>(wproj_t)[i];
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_bq[i] = bqkv[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_bp[i] = bproj[i]; s_ga[i] = gamma[i]; s_be[i] = beta[i]; }
   // zero the padding rows once (rows >= T of Xn / Ks / Vs are never written afterwards)
   for (int i = tid; i < (TP - T) * AB_LD / 2; i += nthr) {
     const int off = T * AB_LD / 2 + i;
     reinterpret_cast<uint32_t*>(Xn)[off] = 0u;
     reinterpret_cast<uint32_t*>(Xr)[off] = 0u;
   }
-  __syncthreads();
+  __syncthreads();  // the only CTA-wide barrier: from here on the teams run independently
 
   const int r0 = warp * 16 + g, r1 = r0 + 8;
-  for (int b = blockIdx.x; b < B2; b += gridDim.x) {
+  for (int b = blockIdx.x * AB_G + team; b < B2; b += gridDim.x * AB_G) {
     const __nv_bfloat16* xb = x + static_cast<size_t>(b) * T * C;
     // ---- raw rows -> shared memory (coalesced 16-byte chunks)
     for (int i = tid; i < T * (C / 8); i += nthr) {
       const int row = i >> 3, seg = i & 7;
       *reinterpret_cast<uint4*>(Xr + row * AB_LD + seg * 8) = *reinterpret_cast<const uint4*>(xb + row * C + seg * 8);
     }
-    __syncthreads();
+    team_sync();
     // ---- GroupNorm statistics: per-channel sums, then per-group mean / rstd
     for (int c = tid; c < C; c += nthr) {
       float s1 = 0.0f, s2 = 0.0f;
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat1
       s_cs[c] = s1;
       s_cs[C + c] = s2;
     }
-    __syncthreads();
+    team_sync();
     if (tid < groups) {
       float s1 = 0.0f, s2 = 0.0f;
       for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { s1 += s_cs[c]; s2 += s_cs[C + c]; }
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat1
       s_gs[2 * tid] = mean;
       s_gs[2 * tid + 1] = 1.0f / sqrtf(var + eps);
     }
-    __syncthreads();
+    team_sync();
     for (int i = tid; i < T * (C / 2); i += nthr) {
       const int row = i / (C / 2), c = (i - row * (C / 2)) * 2;
       const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Xr + row * AB_LD + c));
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat1
       const float bb = (v.y - s_gs[2 * gb]) * s_gs[2 * gb + 1] * s_ga[c + 1] + s_be[c + 1];
       *reinterpret_cast<uint32_t*>(Xn + row * AB_LD + c) = pack_bf16(a, bb);
     }
-    __syncthreads();
+    team_sync();
 
     // ---- q, k, v projections for this warp's 16 rows (A fragments straight from Xn)
     uint32_t xa[4][4];
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat1
       xa[kk][2] = *reinterpret_cast<const uint32_t*>(a0 + 8);
       xa[kk][3] = *reinterpret_cast<const uint32_t*>(a1 + 8);
     }
-    __syncthreads();  // every warp holds its A fragments: Xn may now be overwritten with the keys (and Xr with the values)
+    team_sync();  // every warp holds its A fragments: Xn may now be overwritten with the keys (and Xr with the values)
     auto project8 = [&](const uint32_t (&afrag)[4][4], const __nv_bfloat16* W, int nb, float (&acc)[4]) {
       acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
       const __nv_bfloat16* wr = W + (nb * 8 + g) * AB_LD + 2 * q4;  // B fragment: (k = 2q..2q+1 [+8], n = g)
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat1
         *reinterpret_cast<uint32_t*>(Vs + r1 * AB_LD + c) = pack_bf16(cv[2] + s_bq[2 * C + c], cv[3] + s_bq[2 * C + c + 1]);
       }
     }
-    __syncthreads();
+    team_sync();
 
     // ---- S = Q K^T, softmax over the T valid keys
     float s[2 * T16][4];
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(32 * T16) attn_block_kernel(const __nv_bfloat1
         *reinterpret_cast<uint32_t*>(ob + r1 * C + c) = pack_bf16((xr.x + y[2] + s_bp[c]) * out_scale, (xr.y + y[3] + s_bp[c + 1]) * out_scale);
       }
     }
-    __syncthreads();  // Xr / Ks / Vs are overwritten by the next sample
+    team_sync();  // Xr / Ks / Vs are overwritten by the next sample
   }
 }
 
@@ -390,10 +399,10 @@ int attn_block_launch(const rd_op_attn_block& op, cudaStream_t st) {
   const float scale = 1.0f / sqrtf(static_cast<float>(op.C));
   const int t16 = (op.T + 15) / 16;
   const int tp = 16 * t16;
-  const int smem = (4 * ATT_C * AB_LD + 2 * tp * AB_LD) * 2 + (3 * ATT_C + 3 * ATT_C + 2 * ATT_C + 2 * op.groups) * 4 + 64;
+  const int smem = (4 * ATT_C * AB_LD + AB_G * 2 * tp * AB_LD) * 2 + (3 * ATT_C + 3 * ATT_C + AB_G * (2 * ATT_C + 2 * op.groups)) * 4 + 64;
   const int ctas_per_sm = 227 * 1024 / (smem + 1024) > 4 ? 4 : 227 * 1024 / (smem + 1024);
   int grid = kNumSMs * (ctas_per_sm > 0 ? ctas_per_sm : 1);
-  if (grid > op.B2) grid = op.B2;
+  if (grid * AB_G > op.B2) grid = (op.B2 + AB_G - 1) / AB_G;
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(op.x);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(op.out);
   const __nv_bfloat16* wq = static_cast<const __nv_bfloat16*>(op.wqkv_t);
@@ -407,7 +416,7 @@ int attn_block_launch(const rd_op_attn_block& op, cudaStream_t st) {
       if (e != cudaSuccess) return fail(static_cast<int>(e), "attn_block: %s", cudaGetErrorString(e));                              \
       configured[n] = true;                                                                                                         \
     }                                                                                                                               \
-    attn_block_kernel<n><<<grid, 32 * n, smem, st>>>(x, out, wq, wp, op.bqkv, op.bproj, op.gamma, op.beta, op.B2, op.T, op.groups,   \
+    attn_block_kernel<n><<<grid, 32 * n * AB_G, smem, st>>>(x, out, wq, wp, op.bqkv, op.bproj, op.gamma, op.beta, op.B2, op.T, op.groups,   \
                                                      op.eps, scale, op.out_scale);                                                  \
     break;
     RD_AB_CASE(1) RD_AB_CASE(2) RD_AB_CASE(3) RD_AB_CASE(4) RD_AB_CASE(5) RD_AB_CASE(6) RD_AB_CASE(7) RD_AB_CASE(8)
