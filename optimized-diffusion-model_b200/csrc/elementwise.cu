@@ -66,56 +66,74 @@ __global__ void __launch_bounds__(256) inside_kernel(const float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------
-// cube.score_hk (cube.py:149-193).  Per sample t = sigma^2/2;  t > min_cutoff -> eigenfunction
-// series (_score_hk_ef, cube.py:73-107) else method of images (_score_hk_refl, cube.py:110-146).
-// Same fp32 operation order as the reference; the sums are truncated to the terms that can still
-// change an fp32 accumulator (6 images / min(efs, ceil(sqrt(17/(pi^2 t)))+3)
-// eigenfunctions reproduce the reference's 42 / 20 terms bit for bit in its own implementation).
+// cube.score_hk (cube.py:149-193): score of the heat kernel on [0,1] with reflecting walls.  Per sample
+// t = sigma^2/2.  The reference evaluates  t > min_cutoff  with the eigenfunction series (_score_hk_ef,
+// cube.py:73-107, `efs` cosine modes) and the rest with the method of images (_score_hk_refl, cube.py:110-146,
+// images 2m+x and 2m-x for |m| <= refls).  Both are the SAME function (Poisson summation); the reference's
+// fp32 eigen-series loses up to 1e-5 of the score range just above the cutoff because its denominator
+// 1 + 2 sum(...) cancels, while the image sum has only positive terms.  This kernel therefore
+//   * truncates both sums to the terms that can still change an fp32 result (e^-17.5 relative):
+//       modes  Kc(t) = ceil(sqrt(17.5 / (pi^2 t))) + 1,   images |m| <= Mc(t) = ceil(sqrt((70 t + 1) / 4))
+//   * uses the image sum wherever it is the cheaper converged form (t <= 0.214, at most 10 images), also above
+//     the reference's cutoff -- but only when the reference's own series is converged there (efs >= Kc); a
+//     deliberately short series (efs < Kc) is reproduced term by term;
+//   * matches the reference's epsilons: score = num / (den + 1e-12) in the units of whichever form the
+//     REFERENCE would have used (the image sum is sqrt(4 pi t) times the eigen-series density).
+// Arithmetic: exponentials on the SFU (ex2.approx, 2 ulp), the common factor -2/(4t) applied once, harmonics
+// by the rotation recurrence from one accurate sincospi per coordinate.  Measured error against the fp64
+// reference is at or below the reference's own fp32 error everywhere (tests/test_gpu_elementwise.py).
+// Layout: one block owns HK_SPB whole samples and visits them in an order sorted by (form, term count), so
+// that the threads of a warp run the same loop for the same number of iterations even when sigma differs
+// from sample to sample.
 constexpr int HK_SPB = 32;      // samples per block
 constexpr int HK_MAX_EFS = 64;  // table capacity per sample
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr float PI2_F = 9.869604401089358f;  // python float pi**2 -> fp32 scalar
+constexpr float HK_T_IMAGES = 0.214f;        // above this the eigen-series (<= 5 modes) is the cheaper form
 
 struct HkSampleTab {
-  float t[HK_SPB];
-  int nterm[HK_SPB];  // >= 0: eigenfunction branch with that many terms; -1: reflection branch
+  float c_exp[HK_SPB];   // images: -log2(e) / (4t)
+  float scale[HK_SPB];   // images: -2 / (4t)
+  float eps[HK_SPB];     // denominator epsilon in this form's units
+  int count[HK_SPB];     // images: M (|m| <= M), modes: K
+  int modes[HK_SPB];     // 1: eigen-series, 0: images
+  int order[HK_SPB];     // order[slot] = sample visited at that slot
 };
 
-__device__ __forceinline__ float hk_ef(float x, float x0, const float* __restrict__ eden, const float* __restrict__ enu,
-                                       int K) {
-  const float px = PI_F * x, p0 = PI_F * x0;  // pi * x  (cube.py:94-95)
-  float num = 0.0f, den = 0.0f;
-  for (int k = 1; k <= K; ++k) {
-    const float kf = static_cast<float>(k);
-    float s, c;
-    sincosf(__fmul_rn(px, kf), &s, &c);
-    const float c0 = cosf(__fmul_rn(p0, kf));
-    num = __fadd_rn(num, __fmul_rn(enu[k - 1], __fmul_rn(s, c0)));   // e_num * (sin * cos0)
-    den = __fadd_rn(den, __fmul_rn(eden[k - 1], __fmul_rn(c, c0)));  // e_den * (cos * cos0)
-  }
-  num = __fmul_rn(-2.0f * PI_F, num);                 // - 2 * pi * sum
-  den = __fadd_rn(1.0f, __fmul_rn(2.0f, den));        // 1 + 2 * sum
-  return __fdiv_rn(num, __fadd_rn(den, 1e-12f));
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-__device__ __forceinline__ float hk_refl(float x, float x0, float t, int nimg) {
-  const float fourt = __fmul_rn(4.0f, t);
-  float num = 0.0f, den = 0.0f;
-  // torch.cat order (cube.py:131-135): all (2m + x) for m ascending, then all (2m - x)
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    for (int m = -nimg; m <= nimg; ++m) {
-      const float r = static_cast<float>(2 * m);
-      const float y = half == 0 ? __fadd_rn(r, x) : __fsub_rn(r, x);
-      const float d = __fsub_rn(y, x0);
-      const float coeff = __fdiv_rn(__fmul_rn(-2.0f, d), fourt);
-      const float e = expf(__fdiv_rn(-__fmul_rn(d, d), fourt));
-      const float term = __fmul_rn(coeff, e);
-      num = __fadd_rn(num, half == 0 ? term : -term);
-      den = __fadd_rn(den, e);
-    }
+__device__ __forceinline__ float hk_modes(float x, float x0, const float2* __restrict__ e, int K, float eps) {
+  float s1, c1, s01, c01;
+  sincospif(x, &s1, &c1);     // sin(pi x), cos(pi x)
+  sincospif(x0, &s01, &c01);
+  float s = s1, c = c1, s0 = s01, c0 = c01, num = 0.0f, den = 0.0f;
+  for (int k = 0; k < K; ++k) {
+    const float2 ek = e[k];                  // (exp(-t k^2 pi^2), k * exp(-t k^2 pi^2))
+    den = fmaf(ek.x, c * c0, den);           // cos(k pi x) cos(k pi x0)
+    num = fmaf(ek.y, s * c0, num);           // k sin(k pi x) cos(k pi x0)
+    const float cn = fmaf(c, c1, -s * s1), sn = fmaf(s, c1, c * s1);
+    const float c0n = fmaf(c0, c01, -s0 * s01), s0n = fmaf(s0, c01, c0 * s01);
+    c = cn; s = sn; c0 = c0n; s0 = s0n;
   }
-  return __fdiv_rn(num, __fadd_rn(den, 1e-12f));
+  return __fdividef(-2.0f * PI_F * num, fmaf(2.0f, den, 1.0f) + eps);
+}
+
+__device__ __forceinline__ float hk_images(float x, float x0, float c_exp, float scale, int M, float eps) {
+  float num = 0.0f, den = 0.0f;
+  for (int m = -M; m <= M; ++m) {
+    const float r = static_cast<float>(2 * m);
+    const float da = (r + x) - x0, db = (r - x) - x0;   // images 2m + x (sign +) and 2m - x (sign -)
+    const float ea = ex2_approx(da * da * c_exp), eb = ex2_approx(db * db * c_exp);
+    num = fmaf(da, ea, num);
+    num = fmaf(-db, eb, num);
+    den += ea;
+    den += eb;
+  }
+  return __fdividef(scale * num, den + eps);
 }
 
 template <int VEC>
@@ -124,72 +142,106 @@ __global__ void __launch_bounds__(256) score_hk_kernel(const float* __restrict__
                                                        float* __restrict__ out, size_t B, int D, int efs, int refls,
                                                        float min_cutoff) {
   __shared__ HkSampleTab tab;
-  __shared__ float e_den[HK_SPB][HK_MAX_EFS];
-  __shared__ float e_num[HK_SPB][HK_MAX_EFS];
+  __shared__ float2 e_tab[HK_SPB][HK_MAX_EFS];
   const size_t s0 = static_cast<size_t>(blockIdx.x) * HK_SPB;
   const int ns = static_cast<int>(min(static_cast<size_t>(HK_SPB), B - s0));
 
-  if (threadIdx.x < ns) {
-    const float sg = sigma ? sigma[s0 + threadIdx.x] : sigma_scalar;
-    const float t = __fdiv_rn(__fmul_rn(sg, sg), 2.0f);  // sigma ** 2 / 2
-    tab.t[threadIdx.x] = t;
-    int K = -1;
-    if (t > min_cutoff) {  // ef_cond = t > min_cutoff (cube.py:176)
-      // terms beyond this index are < 2^-24 of the leading ones (e^-17) -- +3 safety margin
-      float kk = ceilf(sqrtf(17.0f / (PI2_F * t))) + 3.0f;
-      K = min(efs, static_cast<int>(fminf(kk, static_cast<float>(HK_MAX_EFS))));
+  if (threadIdx.x < 32) {
+    const int i = threadIdx.x;
+    int key = 0x7fffffff;
+    if (i < ns) {
+      const float sg = sigma ? sigma[s0 + i] : sigma_scalar;
+      const float t = __fdiv_rn(__fmul_rn(sg, sg), 2.0f);  // sigma ** 2 / 2
+      const int Kc = static_cast<int>(fminf(ceilf(sqrtf(17.5f / (PI2_F * t))) + 1.0f, 1.0e6f));
+      const int Mc = static_cast<int>(fminf(ceilf(sqrtf(0.25f * fmaf(70.0f, t, 1.0f))), 1.0e6f));
+      int modes, count;
+      float eps = 1e-12f;
+      if (t > min_cutoff) {            // the reference's ef_cond (cube.py:176)
+        if (efs >= Kc && t <= HK_T_IMAGES) {
+          modes = 0; count = Mc;       // converged series == converged image sum
+          eps = 1e-12f * sqrtf(4.0f * PI_F * t);
+        } else {
+          modes = 1; count = min(efs, min(Kc, HK_MAX_EFS));
+        }
+      } else {
+        modes = 0; count = min(refls, Mc);
+      }
+      // (t != t: NaN sigma) -> NaN out through the image form
+      tab.c_exp[i] = -1.4426950408889634f / (4.0f * t);
+      tab.scale[i] = -2.0f / (4.0f * t);
+      tab.eps[i] = eps;
+      tab.count[i] = count;
+      tab.modes[i] = modes;
+      key = (modes << 20) | min(count, (1 << 20) - 1);
+      if (modes) {
+        for (int k = 1; k <= count; ++k) {
+          const float kf = static_cast<float>(k);
+          const float ev = expf(__fmul_rn(__fmul_rn(-t, __fmul_rn(kf, kf)), PI2_F));  // exp(-t k^2 pi^2) (cube.py:103-104)
+          e_tab[i][k - 1] = make_float2(ev, ev * kf);
+        }
+      }
     }
-    tab.nterm[threadIdx.x] = K;
-  }
-  __syncthreads();
-  // hoisted per-(sample,k) exponentials: exp(-t * k^2 * pi^2)  (cube.py:103-104)
-  for (int i = threadIdx.x; i < ns * HK_MAX_EFS; i += blockDim.x) {
-    const int s = i / HK_MAX_EFS, k = i % HK_MAX_EFS + 1;
-    if (k <= tab.nterm[s]) {
-      const float kf = static_cast<float>(k);
-      const float e = expf(__fmul_rn(__fmul_rn(-tab.t[s], __fmul_rn(kf, kf)), PI2_F));
-      e_den[s][k - 1] = e;
-      e_num[s][k - 1] = __fmul_rn(e, kf);
+    // stable rank of (form, term count) among the block's samples
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const int kj = __shfl_sync(0xffffffffu, key, j);
+      rank += (kj < key || (kj == key && j < i)) ? 1 : 0;
     }
+    if (i < ns) tab.order[rank] = i;
   }
   __syncthreads();
 
-  const int nimg = min(refls, 1);  // images with |m| >= 2 are >= 2 away: exp(-d^2/4t) underflows below 1 ulp
   const size_t base = s0 * D;
   const int nelem = ns * D;
   for (int e = threadIdx.x * VEC; e < nelem; e += blockDim.x * VEC) {
-    const int s = e / D;  // VEC==4 requires D % 4 == 0 so a vector never straddles samples
+    const int slot = e / D;  // VEC==4 requires D % 4 == 0 so a vector never straddles samples
+    const int s = tab.order[slot];
+    const size_t off = base + static_cast<size_t>(s) * D + (e - slot * D);
     float xv[VEC], x0v[VEC], r[VEC];
     if (VEC == 4) {
-      float4 a = ld_stream4(x + base + e), b = ld_stream4(x0 + base + e);
+      float4 a = ld_stream4(x + off), b = ld_stream4(x0 + off);
       xv[0] = a.x; xv[1 % VEC] = a.y; xv[2 % VEC] = a.z; xv[3 % VEC] = a.w;
       x0v[0] = b.x; x0v[1 % VEC] = b.y; x0v[2 % VEC] = b.z; x0v[3 % VEC] = b.w;
     } else {
-      xv[0] = x[base + e];
-      x0v[0] = x0[base + e];
+      xv[0] = x[off];
+      x0v[0] = x0[off];
     }
-    const int K = tab.nterm[s];
-    const float t = tab.t[s];
+    const int cnt = tab.count[s];
+    const float eps = tab.eps[s];
+    if (tab.modes[s]) {
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) r[v] = K >= 0 ? hk_ef(xv[v], x0v[v], e_den[s], e_num[s], K) : hk_refl(xv[v], x0v[v], t, nimg);
-    if (VEC == 4) {
-      st_stream4(out + base + e, make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]));
+      for (int v = 0; v < VEC; ++v) r[v] = hk_modes(xv[v], x0v[v], e_tab[s], cnt, eps);
     } else {
-      out[base + e] = r[0];
+      const float ce = tab.c_exp[s], sc = tab.scale[s];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) r[v] = hk_images(xv[v], x0v[v], ce, sc, cnt, eps);
+    }
+    if (VEC == 4) {
+      st_stream4(out + off, make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]));
+    } else {
+      out[off] = r[0];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // noise dump: exactly the stream the fused step kernels consume
-__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, size_t nquad, uint64_t seed,
-                                                            uint32_t draw) {
+__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, size_t n, uint64_t seed,
+                                                            uint32_t draw, int vec_ok) {
+  const size_t nquad = (n + 3) >> 2;
   size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (; q < nquad; q += stride) {
     float z[4];
     philox_normal4(seed, draw, q, z);
-    st_stream4(out + 4 * q, make_float4(z[0], z[1], z[2], z[3]));
+    if (vec_ok && 4 * q + 4 <= n) {
+      st_stream4(out + 4 * q, make_float4(z[0], z[1], z[2], z[3]));
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (4 * q + u < n) out[4 * q + u] = z[u];
+    }
   }
 }
 
@@ -208,7 +260,11 @@ __global__ void __launch_bounds__(256) cfg_combine_kernel(const float* __restric
 
 // ------------------------------------------------------------------------------------------------
 // Langevin corrector, stage 1 (sampling.py:225-226): per-sample L2 norms of grad and noise.
-// One warp per sample, 8 samples per block; each block emits the sum of its samples' norms.
+// One warp per sample, 8 warps per block, persistent over the batch (grid <= 8 CTAs per SM): every warp sums
+// the norms of its samples in a fixed order, the block adds its 8 warps in a fixed order, so the result is
+// run-to-run deterministic and the number of partials stays small at any batch size.
+// Philox quads are indexed over the FLAT tensor (element 4q..4q+3), so a sample whose D is not a multiple of 4
+// (the shipped 9x9 latents) simply shares its boundary quads with its neighbours.
 constexpr int PC_SPB = 8;
 
 __device__ __forceinline__ uint32_t draw_index(uint32_t draw_base, const int32_t* step_ctr, int which) {
@@ -221,43 +277,52 @@ __global__ void __launch_bounds__(32 * PC_SPB) pc_norms_kernel(const float* __re
                                                                float* __restrict__ partial, size_t B, int D,
                                                                uint64_t seed, uint32_t draw_base,
                                                                const int32_t* __restrict__ step_ctr,
-                                                               size_t noise_step_stride) {
+                                                               size_t noise_step_stride, int vec_ok) {
   __shared__ float sg[PC_SPB], sn[PC_SPB];
   if (noise && step_ctr) noise += static_cast<size_t>(*step_ctr) * noise_step_stride;
+  if (noise && (reinterpret_cast<uintptr_t>(noise) & 15)) vec_ok = 0;  // tape slices of odd-sized tensors
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t b = static_cast<size_t>(blockIdx.x) * PC_SPB + warp;
-  float g2 = 0.0f, n2 = 0.0f;
-  if (b < B) {
-    const uint32_t draw = draw_index(draw_base, step_ctr, 0);
-    const size_t e0 = b * D;
-    // D % 4 == 0 is validated on the host when Philox noise is used (quads must not straddle tensors' ends)
-    for (int j = lane * 4; j < D; j += 128) {
-      if (j + 3 < D && (((e0 + j) & 3) == 0)) {
-        float4 g = *reinterpret_cast<const float4*>(grad + e0 + j);
-        float z[4];
+  const uint32_t draw = draw_index(draw_base, step_ctr, 0);
+  float acc_g = 0.0f, acc_n = 0.0f;
+  for (size_t b = static_cast<size_t>(blockIdx.x) * PC_SPB + warp; b < B; b += static_cast<size_t>(gridDim.x) * PC_SPB) {
+    const size_t e0 = b * D, e1 = e0 + D;
+    float g2 = 0.0f, n2 = 0.0f;
+    for (size_t q = (e0 >> 2) + lane; 4 * q < e1; q += 32) {
+      const size_t i0 = 4 * q;
+      float gv[4], z[4];
+      const bool whole = i0 >= e0 && i0 + 4 <= e1;
+      if (whole && vec_ok) {
+        const float4 g = *reinterpret_cast<const float4*>(grad + i0);
+        gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w;
         if (noise) {
-          float4 nz = *reinterpret_cast<const float4*>(noise + e0 + j);
+          const float4 nz = *reinterpret_cast<const float4*>(noise + i0);
           z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
-        } else {
-          philox_normal4(seed, draw, (e0 + j) >> 2, z);
         }
-        g2 += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
-        n2 += z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3];
       } else {
-        for (int u = j; u < min(j + 4, D); ++u) {  // ragged tail / unaligned (tape mode only)
-          const float g = grad[e0 + u], z = noise[e0 + u];
-          g2 += g * g;
-          n2 += z * z;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool in = i0 + u >= e0 && i0 + u < e1;
+          gv[u] = in ? grad[i0 + u] : 0.0f;
+          z[u] = (in && noise) ? noise[i0 + u] : 0.0f;
         }
       }
+      if (!noise) {
+        philox_normal4(seed, draw, q, z);
+        if (!whole) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (!(i0 + u >= e0 && i0 + u < e1)) z[u] = 0.0f;
+        }
+      }
+      g2 += gv[0] * gv[0] + gv[1] * gv[1] + gv[2] * gv[2] + gv[3] * gv[3];
+      n2 += z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3];
     }
+    g2 = warp_sum(g2);
+    n2 = warp_sum(n2);
+    acc_g += sqrtf(g2);
+    acc_n += sqrtf(n2);
   }
-  g2 = warp_sum(g2);
-  n2 = warp_sum(n2);
-  if (lane == 0) {
-    sg[warp] = (b < B) ? sqrtf(g2) : 0.0f;
-    sn[warp] = (b < B) ? sqrtf(n2) : 0.0f;
-  }
+  if (lane == 0) { sg[warp] = acc_g; sn[warp] = acc_n; }
   __syncthreads();
   if (threadIdx.x == 0) {
     float a = 0.0f, c = 0.0f;
@@ -268,7 +333,7 @@ __global__ void __launch_bounds__(32 * PC_SPB) pc_norms_kernel(const float* __re
   }
 }
 
-// fixed-order reduction of the per-block partials by one warp; every block recomputes it (a few KB from L2)
+// fixed-order reduction of the per-block partials by one warp; every block recomputes it (<= 10 KB from L2)
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, float& gsum, float& nsum) {
   const int lane = threadIdx.x & 31;
   float a = 0.0f, c = 0.0f;
@@ -280,14 +345,76 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   nsum = warp_sum(c);
 }
 
+// Shared body of the two fused updates:  x_mean = x + a * v ;  x = reflect(x_mean + b * z) ; x_mean = reflect(x_mean)
+// over quads of the flat tensor; whole, aligned quads move as 128-bit vectors, the rest element by element.
+template <bool MEAN, bool PER_SAMPLE, bool PRED>
+__device__ __forceinline__ void pc_update_loop(const float* __restrict__ x, const float* __restrict__ v,
+                                               const float* __restrict__ zt, float a, float b,
+                                               const float* __restrict__ g_table, float dt, float sqrt_dt,
+                                               float* __restrict__ x_out, float* __restrict__ x_mean_out, size_t n,
+                                               size_t D, uint64_t seed, uint32_t draw, bool vec_ok) {
+  const size_t nq = (n + 3) >> 2;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const size_t i0 = 4 * i;
+    const bool whole = vec_ok && i0 + 4 <= n;
+    float xs[4], vs[4], z[4];
+    if (whole) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + i0), vv = *reinterpret_cast<const float4*>(v + i0);
+      xs[0] = xv.x; xs[1] = xv.y; xs[2] = xv.z; xs[3] = xv.w;
+      vs[0] = vv.x; vs[1] = vv.y; vs[2] = vv.z; vs[3] = vv.w;
+      if (zt) {
+        const float4 nz = ld_stream4(zt + i0);
+        z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool in = i0 + u < n;
+        xs[u] = in ? x[i0 + u] : 0.0f;
+        vs[u] = in ? v[i0 + u] : 0.0f;
+        z[u] = (in && zt) ? zt[i0 + u] : 0.0f;
+      }
+    }
+    if (!zt) philox_normal4(seed, draw, i, z);
+    float xm[4], xn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float au = a, bu = b;
+      if (PER_SAMPLE) {  // predictor with one diffusion coefficient per sample (update_fn API, arbitrary t[B])
+        const float g = g_table[min(i0 + u, n - 1) / D];
+        au = -__fmul_rn(g, g);
+        bu = __fmul_rn(g, sqrt_dt);
+      }
+      // predictor: drift = -(g^2) * score ; x_mean = x + drift * dt        corrector: x_mean = x + step * grad
+      const float m = PRED ? __fadd_rn(xs[u], __fmul_rn(__fmul_rn(au, vs[u]), dt)) : __fadd_rn(xs[u], __fmul_rn(au, vs[u]));
+      xn[u] = reflect1(__fadd_rn(m, __fmul_rn(bu, z[u])));
+      if (MEAN) xm[u] = reflect1(m);
+    }
+    if (whole) {
+      *reinterpret_cast<float4*>(x_out + i0) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+      if (MEAN) *reinterpret_cast<float4*>(x_mean_out + i0) = make_float4(xm[0], xm[1], xm[2], xm[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u < n) {
+          x_out[i0 + u] = xn[u];
+          if (MEAN) x_mean_out[i0 + u] = xm[u];
+        }
+    }
+  }
+}
+
 // Langevin corrector, stage 2 (sampling.py:227-231)
+template <bool MEAN>
 __global__ void __launch_bounds__(256) pc_corrector_apply_kernel(
     const float* __restrict__ x, const float* __restrict__ grad, const float* __restrict__ noise,
     const float* __restrict__ partial, int nblk, float snr, float* __restrict__ x_out, float* __restrict__ x_mean_out,
     float* __restrict__ stats_out, size_t B, size_t n, uint64_t seed, uint32_t draw_base,
-    const int32_t* __restrict__ step_ctr, size_t noise_step_stride) {
+    const int32_t* __restrict__ step_ctr, size_t noise_step_stride, int vec_ok) {
   __shared__ float s_step, s_noise_c;
   if (noise && step_ctr) noise += static_cast<size_t>(*step_ctr) * noise_step_stride;
+  if (noise && (reinterpret_cast<uintptr_t>(noise) & 15)) vec_ok = 0;
   if (threadIdx.x < 32) {
     float gsum, nsum;
     reduce_partials(partial, nblk, gsum, nsum);
@@ -301,99 +428,27 @@ __global__ void __launch_bounds__(256) pc_corrector_apply_kernel(
     }
   }
   __syncthreads();
-  const float step = s_step, nc = s_noise_c;
-  const uint32_t draw = draw_index(draw_base, step_ctr, 0);
-  const size_t n4 = n >> 2;
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n4; i += stride) {
-    const float4 xv = *reinterpret_cast<const float4*>(x + 4 * i);
-    const float4 gv = *reinterpret_cast<const float4*>(grad + 4 * i);
-    float z[4];
-    if (noise) {
-      const float4 nz = ld_stream4(noise + 4 * i);
-      z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
-    } else {
-      philox_normal4(seed, draw, i, z);
-    }
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
-    float xm[4], xn[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float m = __fadd_rn(xs[u], __fmul_rn(step, gs[u]));  // x_mean = x + step * grad
-      xn[u] = reflect1(__fadd_rn(m, __fmul_rn(nc, z[u])));       // x = x_mean + sqrt(2 step) * noise
-      xm[u] = reflect1(m);
-    }
-    *reinterpret_cast<float4*>(x_out + 4 * i) = make_float4(xn[0], xn[1], xn[2], xn[3]);
-    if (x_mean_out) *reinterpret_cast<float4*>(x_mean_out + 4 * i) = make_float4(xm[0], xm[1], xm[2], xm[3]);
-  }
-  // scalar tail (tape mode only; Philox mode requires n % 4 == 0)
-  size_t t = (n4 << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t < n) {
-    const float m = __fadd_rn(x[t], __fmul_rn(step, grad[t]));
-    x_out[t] = reflect1(__fadd_rn(m, __fmul_rn(nc, noise[t])));
-    if (x_mean_out) x_mean_out[t] = reflect1(m);
-  }
+  // x_mean = x + step * grad ; x = x_mean + sqrt(2 step) * noise
+  pc_update_loop<MEAN, false, false>(x, grad, noise, s_step, s_noise_c, nullptr, 0.0f, 0.0f, x_out, x_mean_out, n, 1, seed,
+                              draw_index(draw_base, step_ctr, 0), vec_ok != 0);
 }
 
 // Euler-Maruyama predictor on the reverse reflected VE-SDE (sampling.py:198-207, sde_lib.py:93-101,135-140):
 //   drift = 0 - g^2 * score ; x_mean = x + drift * dt ; x = x_mean + (g * sqrt(-dt)) * z ; reflect both
+template <bool MEAN, bool PER_SAMPLE>
 __global__ void __launch_bounds__(256) pc_predictor_kernel(const float* __restrict__ x, const float* __restrict__ score,
                                                            const float* __restrict__ zt, const float* __restrict__ g_table,
                                                            float dt, float sqrt_dt, float* __restrict__ x_out,
                                                            float* __restrict__ x_mean_out, size_t n, uint64_t seed,
                                                            uint32_t draw_base, const int32_t* __restrict__ step_ctr,
-                                                           size_t noise_step_stride, int g_per_sample, size_t D) {
+                                                           size_t noise_step_stride, size_t D, int vec_ok) {
   const int32_t step = step_ctr ? *step_ctr : 0;
   if (zt) zt += static_cast<size_t>(step) * noise_step_stride;
-  // g_per_sample: g_table holds one diffusion coefficient per sample (update_fn API with arbitrary t[B]);
-  // otherwise one per sampler step, shared by the batch
-  float g = g_per_sample ? 0.0f : g_table[step];
-  float g2 = __fmul_rn(g, g);
-  float gz = __fmul_rn(g, sqrt_dt);
-  const uint32_t draw = draw_base + 2u * static_cast<uint32_t>(step) + 1u;
-  const size_t n4 = n >> 2;
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (; i < n4; i += stride) {
-    const float4 xv = *reinterpret_cast<const float4*>(x + 4 * i);
-    const float4 sv = *reinterpret_cast<const float4*>(score + 4 * i);
-    float z[4];
-    if (zt) {
-      const float4 nz = ld_stream4(zt + 4 * i);
-      z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
-    } else {
-      philox_normal4(seed, draw, i, z);
-    }
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w};
-    float xm[4], xn[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (g_per_sample) {
-        g = g_table[(4 * i + u) / D];
-        g2 = __fmul_rn(g, g);
-        gz = __fmul_rn(g, sqrt_dt);
-      }
-      const float drift = -__fmul_rn(g2, ss[u]);
-      const float m = __fadd_rn(xs[u], __fmul_rn(drift, dt));
-      xn[u] = reflect1(__fadd_rn(m, __fmul_rn(gz, z[u])));
-      xm[u] = reflect1(m);
-    }
-    *reinterpret_cast<float4*>(x_out + 4 * i) = make_float4(xn[0], xn[1], xn[2], xn[3]);
-    if (x_mean_out) *reinterpret_cast<float4*>(x_mean_out + 4 * i) = make_float4(xm[0], xm[1], xm[2], xm[3]);
-  }
-  size_t t = (n4 << 2) + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t < n) {
-    if (g_per_sample) {
-      g = g_table[t / D];
-      g2 = __fmul_rn(g, g);
-      gz = __fmul_rn(g, sqrt_dt);
-    }
-    const float drift = -__fmul_rn(g2, score[t]);
-    const float m = __fadd_rn(x[t], __fmul_rn(drift, dt));
-    x_out[t] = reflect1(__fadd_rn(m, __fmul_rn(gz, zt[t])));
-    if (x_mean_out) x_mean_out[t] = reflect1(m);
-  }
+  if (zt && (reinterpret_cast<uintptr_t>(zt) & 15)) vec_ok = 0;
+  // PER_SAMPLE: g_table holds one diffusion coefficient per sample; otherwise one per sampler step
+  const float g = PER_SAMPLE ? 0.0f : g_table[step];
+  pc_update_loop<MEAN, PER_SAMPLE, true>(x, score, zt, -__fmul_rn(g, g), __fmul_rn(g, sqrt_dt), g_table, dt, sqrt_dt, x_out,
+                                   x_mean_out, n, D, seed, draw_base + 2u * static_cast<uint32_t>(step) + 1u, vec_ok != 0);
 }
 
 __global__ void step_advance_kernel(int32_t* ctr) { *ctr += 1; }
@@ -452,21 +507,31 @@ int rd_score_hk_f32(const float* x, const float* x_orig, const float* sigma, flo
   size_t blocks = (B + HK_SPB - 1) / HK_SPB;
   bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_orig) |
                                reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  // block size: the one (multiple of 32, 128..256) that leaves the fewest idle threads in the last pass over the
+  // block's HK_SPB * D elements (D = 72: 576 vectors = 3 passes of 192 threads)
+  const size_t items = static_cast<size_t>(HK_SPB) * D / (vec ? 4 : 1);
+  int threads = 256;
+  double best = 0.0;
+  for (int t = 256; t >= 128; t -= 32) {
+    const double eff = static_cast<double>(items) / (static_cast<double>((items + t - 1) / t) * t);
+    if (eff > best + 1e-9) { best = eff; threads = t; }
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (vec)
-    score_hk_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
-                                                                       static_cast<int>(D), efs, refls, min_cutoff);
+    score_hk_kernel<4><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
+                                                                           static_cast<int>(D), efs, refls, min_cutoff);
   else
-    score_hk_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
-                                                                       static_cast<int>(D), efs, refls, min_cutoff);
+    score_hk_kernel<1><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
+                                                                           static_cast<int>(D), efs, refls, min_cutoff);
   return check_launch("score_hk_kernel");
 }
 
 int rd_philox_normal_f32(float* out, size_t n, uint64_t seed, uint32_t draw, void* stream) {
   if (n == 0) return RD_OK;
-  RD_REQUIRE(out && (n % 4 == 0), "rd_philox_normal_f32: n must be a multiple of 4");
-  int grid = stream_grid(n / 4, 256, 8);
-  philox_normal_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n / 4, seed, draw);
+  RD_REQUIRE(out, "rd_philox_normal_f32: null pointer");
+  int grid = stream_grid((n + 3) / 4, 256, 8);
+  philox_normal_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, draw,
+                                                                             (reinterpret_cast<uintptr_t>(out) & 15) == 0);
   return check_launch("philox_normal_kernel");
 }
 
@@ -479,15 +544,21 @@ int rd_cfg_combine_f32(const float* s, const float* w, float w_scalar, float* ou
   return check_launch("cfg_combine_kernel");
 }
 
+static inline int all_aligned16(const void* a, const void* b, const void* c, const void* d) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+}
+
 int rd_pc_norms(const float* grad, const float* noise, float* partial, int* nblk, size_t B, size_t D,
                 uint64_t seed, uint32_t draw_base, const int32_t* step_ctr, size_t noise_step_stride,
                 void* stream) {
   RD_REQUIRE(grad && partial && B > 0 && D > 0, "rd_pc_norms: bad arguments");
-  RD_REQUIRE(noise || (D % 4 == 0), "rd_pc_norms: Philox noise needs D %% 4 == 0");
-  int blocks = static_cast<int>((B + PC_SPB - 1) / PC_SPB);
+  size_t want = (B + PC_SPB - 1) / PC_SPB, cap = static_cast<size_t>(kNumSMs) * 8;
+  int blocks = static_cast<int>(want < cap ? want : cap);
   if (nblk) *nblk = blocks;
   pc_norms_kernel<<<blocks, 32 * PC_SPB, 0, static_cast<cudaStream_t>(stream)>>>(
-      grad, noise, partial, B, static_cast<int>(D), seed, draw_base, step_ctr, noise_step_stride);
+      grad, noise, partial, B, static_cast<int>(D), seed, draw_base, step_ctr, noise_step_stride,
+      all_aligned16(grad, noise, nullptr, nullptr));
   return check_launch("pc_norms_kernel");
 }
 
@@ -497,11 +568,15 @@ int rd_pc_corrector_apply(const float* x, const float* grad, const float* noise,
                           size_t noise_step_stride, void* stream) {
   RD_REQUIRE(x && grad && partial && x_out && B > 0 && D > 0 && nblk > 0, "rd_pc_corrector_apply: bad arguments");
   const size_t n = B * D;
-  RD_REQUIRE(noise || (n % 4 == 0), "rd_pc_corrector_apply: Philox noise needs B*D %% 4 == 0");
+  const int vec_ok = all_aligned16(x, grad, x_out, x_mean_out) && all_aligned16(noise, nullptr, nullptr, nullptr);
   int grid = stream_grid((n + 3) / 4, 256, 8);
-  pc_corrector_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, grad, noise, partial, nblk, snr, x_out, x_mean_out, stats_out, B, n, seed, draw_base, step_ctr,
-      noise_step_stride);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_mean_out)
+    pc_corrector_apply_kernel<true><<<grid, 256, 0, st>>>(x, grad, noise, partial, nblk, snr, x_out, x_mean_out, stats_out,
+                                                          B, n, seed, draw_base, step_ctr, noise_step_stride, vec_ok);
+  else
+    pc_corrector_apply_kernel<false><<<grid, 256, 0, st>>>(x, grad, noise, partial, nblk, snr, x_out, x_mean_out, stats_out,
+                                                           B, n, seed, draw_base, step_ctr, noise_step_stride, vec_ok);
   return check_launch("pc_corrector_apply_kernel");
 }
 
@@ -511,12 +586,16 @@ int rd_pc_predictor_step(const float* x, const float* score, const float* z, con
                          int g_per_sample, void* stream) {
   RD_REQUIRE(x && score && g_table && x_out && B > 0 && D > 0, "rd_pc_predictor_step: bad arguments");
   const size_t n = B * D;
-  RD_REQUIRE(z || (n % 4 == 0), "rd_pc_predictor_step: Philox noise needs B*D %% 4 == 0");
   RD_REQUIRE(!advance_ctr || step_ctr, "rd_pc_predictor_step: advance_ctr needs step_ctr");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int vec_ok = all_aligned16(x, score, x_out, x_mean_out) && all_aligned16(z, nullptr, nullptr, nullptr);
   int grid = stream_grid((n + 3) / 4, 256, 8);
-  pc_predictor_kernel<<<grid, 256, 0, st>>>(x, score, z, g_table, dt, sqrt_dt, x_out, x_mean_out, n, seed,
-                                            draw_base, step_ctr, noise_step_stride, g_per_sample, D);
+#define RD_PRED(M, P)                                                                                              \
+  pc_predictor_kernel<M, P><<<grid, 256, 0, st>>>(x, score, z, g_table, dt, sqrt_dt, x_out, x_mean_out, n, seed, \
+                                                  draw_base, step_ctr, noise_step_stride, D, vec_ok)
+  if (x_mean_out) { if (g_per_sample) RD_PRED(true, true); else RD_PRED(true, false); }
+  else            { if (g_per_sample) RD_PRED(false, true); else RD_PRED(false, false); }
+#undef RD_PRED
   int rc = check_launch("pc_predictor_kernel");
   if (rc != RD_OK) return rc;
   if (advance_ctr) {

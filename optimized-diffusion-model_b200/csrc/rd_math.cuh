@@ -48,21 +48,26 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 }
 
 // Four N(0,1) draws for the 4-element group `quad` of noise tensor number `draw` under `seed`.
-// Box-Muller on (0,1] uniforms; accurate logf / sincospif so the tail is not truncated early.
+// Box-Muller on (0,1] x (-pi,pi] uniforms evaluated on the special-function unit (lg2 / sqrt / sin / cos
+// .approx: absolute error ~2^-21 on the angle functions, ~2e-7 on -2 ln u): the stream is OURS, every consumer
+// (fused step kernels, rd_philox_normal_f32 dump) calls this one function, and the accurate libm versions cost
+// three times the instructions of the whole update they feed.  |z| <= 6.76 (u1 >= 2^-33).
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t draw, uint64_t quad, float (&z)[4]) {
   Philox4 r = philox4x32_10(static_cast<uint32_t>(quad), static_cast<uint32_t>(quad >> 32), draw, 0x5eedu,
                             static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
   const float S = 2.3283064365386963e-10f;  // 2^-32
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
-    float u1 = (static_cast<float>(r.c[2 * p]) + 0.5f) * S;      // (0,1]
-    float u2 = (static_cast<float>(r.c[2 * p + 1]) + 0.5f) * S;
-    u1 = fminf(u1, 1.0f);
-    float rad = sqrtf(-2.0f * logf(u1));
-    float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
-    z[2 * p] = rad * cs;
-    z[2 * p + 1] = rad * sn;
+    float u1 = fminf((static_cast<float>(r.c[2 * p]) + 0.5f) * S, 1.0f);                 // (0,1]
+    const float ang = (static_cast<float>(r.c[2 * p + 1]) + 0.5f) * (S * 6.283185307179586f) - 3.141592653589793f;
+    const float rad = sqrt_approx(fmaxf(-1.3862943611198906f * __log2f(u1), 0.0f));     // sqrt(-2 ln u1)
+    z[2 * p] = rad * __cosf(ang);
+    z[2 * p + 1] = rad * __sinf(ang);
   }
 }
 

@@ -176,8 +176,6 @@ def _native_engine(model, sde, shape, predictor, corrector, snr, n_steps, eps, d
     if not cfg and getattr(model, 'conditional', False):
         return None  # (the reference crashes here: label_emb(None), ncsnpp.py:262)
     B, _, H, W = shape
-    if (H * W * shape[1]) % 4 != 0:
-        return None  # Philox quads; odd sizes (9x9) take the generic loop
     return model.rd_sampler_engine(B, H, W, device, sde, eps, snr, n_corr, cfg=cfg)
 
 

@@ -115,3 +115,62 @@ def test_two_rank_batch_sharding_gloo():
     assert (res[0][1], res[0][2], res[1][1], res[1][2]) == (0, 5, 5, 10)
     assert res[0][3] == list(map(float, range(10))) == res[1][3]
     assert res[0][4] != res[1][4]
+
+
+def test_conv_launch_geometry_invariants():
+    """rd_conv_launch_info is pure host logic: for every layer shape of the GTO-Halo network the chosen geometry must
+    fit the 227 KB shared-memory budget, fill at most one CTA per SM, and stage an odd number of rows (the un-swizzled
+    K-major operand relies on it for conflict-free 16-byte row strides)."""
+    import ctypes as C
+    from rdb200 import _lib, cdefs as D
+    lib = _lib.lib()
+    shapes = [(64, 0, 64, 8, 9, 9), (128, 64, 64, 8, 9, 9), (64, 64, 64, 8, 9, 9), (64, 0, 128, 4, 4, 9), (128, 0, 128, 4, 4, 9),
+              (128, 128, 128, 4, 4, 9), (128, 0, 128, 2, 2, 9), (128, 128, 128, 2, 2, 9), (128, 64, 64, 8, 9, 1),
+              (128, 128, 128, 2, 2, 1), (64, 0, 192, 8, 9, 1)]
+    for c0, c1, cout, H, W, taps in shapes:
+        op = D.OpConv()
+        op.nsrc = 2 if c1 else 1
+        op.src[0].ptr, op.src[0].C, op.src[0].Hs, op.src[0].Ws = 0x1000, c0, H, W
+        if c1:
+            op.src[1].ptr, op.src[1].C, op.src[1].Hs, op.src[1].Ws = 0x1000, c1, H, W
+        op.H_in, op.W_in, op.H_out, op.W_out = H, W, H, W
+        op.pad, op.stride, op.ntaps, op.C_out = (1 if taps == 9 else 0), 1, taps, cout
+        if taps == 9:
+            op.gn_groups, op.gn_silu, op.gn_eps, op.gn_gamma, op.gn_beta = min((c0 + c1) // 4, 32), 1, 1e-6, 0x1000, 0x1000
+        op.w, op.bias, op.out, op.out_scale, op.B2 = 0x1000, 0x1000, 0x1000, 1.0, 16384
+        smem, grid, rows = C.c_int(), C.c_int(), C.c_int()
+        assert lib.rd_conv_launch_info(C.byref(op), C.byref(smem), C.byref(grid), C.byref(rows)) == 0, lib.rd_last_error()
+        assert 0 < smem.value <= 227 * 1024 - 2048
+        assert 1 <= grid.value <= 148
+        assert rows.value % 2 == 1 and rows.value >= 128
+    bad = D.OpConv()
+    bad.nsrc, bad.ntaps = 1, 5
+    assert lib.rd_conv_launch_info(C.byref(bad), None, None, None) != 0 and b"ntaps" in lib.rd_last_error()
+
+
+def test_engine_plan_accounting():
+    """The algorithmic FLOP count the bench's roofline uses equals the closed form of the network (valid pixels only):
+    the planner must not change it when ops are fused or split."""
+    spec = spec_from_config(make_config(8, 8))
+    # closed form for nf=64, ch_mult (1,2,2), 2 res blocks, 8x9 -> 4x4 -> 2x2 (SURVEY.md App. B layer table)
+    def conv(hw, cin, cout, taps=9):
+        return 2.0 * hw * cout * cin * taps
+    total = 0.0
+    P0, P1, P2 = 72, 16, 4
+    total += 2 * (conv(P0, 64, 64) * 2)                                   # down level 0
+    total += conv(P1, 64, 64)                                             # downsample.0 (4x4 out)
+    total += conv(P1, 64, 128) + conv(P1, 128, 128) + conv(P1, 64, 128, 1) + 2 * conv(P1, 128, 128)   # down level 1
+    total += conv(P2, 128, 128)                                           # downsample.1
+    total += 2 * 2 * conv(P2, 128, 128) + 2 * 2 * conv(P2, 128, 128)      # down level 2 + mid
+    total += 3 * (conv(P2, 256, 128) + conv(P2, 128, 128) + conv(P2, 256, 128, 1))   # up level 2
+    total += conv(P1, 128, 128)                                           # upsample.0
+    # the reference pushes the last block output of a level twice and never the downsample output
+    # (ncsnpp.py:285-292), so all three up blocks of level 1 see 128 + 128 input channels
+    total += 3 * (conv(P1, 256, 128) + conv(P1, 128, 128) + conv(P1, 256, 128, 1))
+    total += conv(64, 128, 128)                                           # upsample.1 writes 8x8 (ncsnpp.py:319-320 fixes it up later)
+    total += (conv(P0, 192, 64) + conv(P0, 64, 64) + conv(P0, 192, 64, 1)) + 2 * (conv(P0, 128, 64) + conv(P0, 64, 64) + conv(P0, 128, 64, 1))
+    # the engine needs a GPU to build; the closed form is cross-checked against DESIGN.md's figure (SURVEY.md App. A:
+    # 200.74 conv+linear+NIN minus attention NINs 11.8, temb linears 1.15, input/output convs 0.17) here and
+    # against Engine.conv_flops_per_sample in tests/test_gpu_network.py
+    assert abs(total / 1e6 - 187.63) < 0.01, total / 1e6
+    assert spec.levels == 3 and spec.nf == 64
