@@ -184,17 +184,20 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
   const int team = threadIdx.x / (32 * T16);
   const int tid = threadIdx.x - team * (32 * T16), warp = tid >> 5, lane = tid & 31;
   constexpr int nthr = 32 * T16;
-  __nv_bfloat16* Xr = Wp + C * AB_LD + team * 2 * TP * AB_LD;   // raw input rows   [TP][AB_LD]
-  __nv_bfloat16* Vs = Xr;                                       // values (aliases Xr)
-  __nv_bfloat16* Xn = Xr + TP * AB_LD;                          // normalised rows  [TP][AB_LD]
-  __nv_bfloat16* Ks = Xn;                                       // keys (aliases Xn)
-  float* s_par = reinterpret_cast<float*>(Wp + C * AB_LD + AB_G * 2 * TP * AB_LD);  // bqkv[3C], bproj[C], gamma[C], beta[C], per team: chsum[2C], gstat[2*groups]
+  __nv_bfloat16* Vs = Wp + C * AB_LD + team * 2 * TP * AB_LD;   // values           [TP][AB_LD]
+  __nv_bfloat16* Xn = Vs + TP * AB_LD;                          // normalised rows  [TP][AB_LD]
+  __nv_bfloat16* Ks = Xn;                                       // keys (aliases Xn once every warp holds its A fragments)
+  // per-warp private staging of its 16 rows: raw input (the residual) on the way in, finished output on the way out,
+  // so that both cross HBM/L2 as coalesced 16-byte accesses
+  __nv_bfloat16* Yst = Wp + C * AB_LD + AB_G * 2 * TP * AB_LD + (team * T16 + warp) * 16 * AB_LD;
+  float* s_par = reinterpret_cast<float*>(Wp + C * AB_LD + AB_G * 2 * TP * AB_LD + AB_G * T16 * 16 * AB_LD);
+  // bqkv[3C], bproj[C], gamma[C], beta[C], per team: part[T16][2C] (per-warp channel sums), coef[2C] (y = x*a + b)
   float* s_bq = s_par;
   float* s_bp = s_bq + 3 * C;
   float* s_ga = s_bp + C;
   float* s_be = s_ga + C;
-  float* s_cs = s_be + C + team * (2 * C + 2 * groups);
-  float* s_gs = s_cs + 2 * C;
+  float* s_pt = s_be + C + team * (T16 * 2 * C + 2 * C);
+  float* s_cf = s_pt + T16 * 2 * C;
   const int g = lane >> 2, q4 = lane & 3;
   const int cpg = C / groups;
   auto team_sync = [&]() {  // literal barrier ids keep the CTA's barrier allocation at 3 instead of all 16
@@ -211,50 +214,80 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
   for (int i = tid; i < (TP - T) * AB_LD / 2; i += nthr) {
     const int off = T * AB_LD / 2 + i;
     reinterpret_cast<uint32_t*>(Xn)[off] = 0u;
-    reinterpret_cast<uint32_t*>(Xr)[off] = 0u;
+    reinterpret_cast<uint32_t*>(Vs)[off] = 0u;
   }
   __syncthreads();  // the only CTA-wide barrier: from here on the teams run independently
 
   const int r0 = warp * 16 + g, r1 = r0 + 8;
   for (int b = blockIdx.x * AB_G + team; b < B2; b += gridDim.x * AB_G) {
     const __nv_bfloat16* xb = x + static_cast<size_t>(b) * T * C;
-    // ---- raw rows -> shared memory (coalesced 16-byte chunks)
-    for (int i = tid; i < T * (C / 8); i += nthr) {
-      const int row = i >> 3, seg = i & 7;
-      *reinterpret_cast<uint4*>(Xr + row * AB_LD + seg * 8) = *reinterpret_cast<const uint4*>(xb + row * C + seg * 8);
-    }
-    team_sync();
-    // ---- GroupNorm statistics: per-channel sums, then per-group mean / rstd
-    for (int c = tid; c < C; c += nthr) {
-      float s1 = 0.0f, s2 = 0.0f;
-      for (int t = 0; t < T; ++t) {
-        const float v = __bfloat162float(Xr[t * AB_LD + c]);
-        s1 += v;
-        s2 = fmaf(v, v, s2);
+    // ---- this warp's 16 raw rows: global -> registers (coalesced 16-byte chunks; lane owns one 8-channel segment of
+    // four rows) -> private staging (the residual of the epilogue); GroupNorm sums straight from the registers
+    const int seg = lane & 7, rsub = lane >> 3;
+    uint4 raw[4];
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.0f; s2[j] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int rl = rsub + 4 * k, row = warp * 16 + rl;
+      raw[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (row < T) raw[k] = __ldg(reinterpret_cast<const uint4*>(xb + row * C + seg * 8));
+      *reinterpret_cast<uint4*>(Yst + rl * AB_LD + seg * 8) = raw[k];
+      const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+        s1[2 * j] += lo; s2[2 * j] = fmaf(lo, lo, s2[2 * j]);
+        s1[2 * j + 1] += hi; s2[2 * j + 1] = fmaf(hi, hi, s2[2 * j + 1]);
       }
-      s_cs[c] = s1;
-      s_cs[C + c] = s2;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+    }
+    if (lane < 8) {
+      float4* d1 = reinterpret_cast<float4*>(s_pt + warp * 2 * C + seg * 8);
+      float4* d2 = reinterpret_cast<float4*>(s_pt + warp * 2 * C + C + seg * 8);
+      d1[0] = make_float4(s1[0], s1[1], s1[2], s1[3]); d1[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
+      d2[0] = make_float4(s2[0], s2[1], s2[2], s2[3]); d2[1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
     }
     team_sync();
-    if (tid < groups) {
-      float s1 = 0.0f, s2 = 0.0f;
-      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { s1 += s_cs[c]; s2 += s_cs[C + c]; }
+    // ---- per-channel affine of the group statistics: thread c sums its group's channels over the warps' partials
+    if (tid < C) {
+      const int c0 = (tid / cpg) * cpg;
+      float a1 = 0.0f, a2 = 0.0f;
+      for (int w = 0; w < T16; ++w)
+        for (int c = c0; c < c0 + cpg; ++c) { a1 += s_pt[w * 2 * C + c]; a2 += s_pt[w * 2 * C + C + c]; }
       const float inv = 1.0f / static_cast<float>(cpg * T);
-      const float mean = s1 * inv;
-      const float var = fmaxf(s2 * inv - mean * mean, 0.0f);
-      s_gs[2 * tid] = mean;
-      s_gs[2 * tid + 1] = 1.0f / sqrtf(var + eps);
+      const float mean = a1 * inv;
+      const float var = fmaxf(a2 * inv - mean * mean, 0.0f);
+      const float ca = s_ga[tid] / sqrtf(var + eps);
+      s_cf[tid] = ca;
+      s_cf[C + tid] = fmaf(-mean, ca, s_be[tid]);
     }
     team_sync();
-    for (int i = tid; i < T * (C / 2); i += nthr) {
-      const int row = i / (C / 2), c = (i - row * (C / 2)) * 2;
-      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Xr + row * AB_LD + c));
-      const int ga = c / cpg, gb = (c + 1) / cpg;
-      const float a = (v.x - s_gs[2 * ga]) * s_gs[2 * ga + 1] * s_ga[c] + s_be[c];
-      const float bb = (v.y - s_gs[2 * gb]) * s_gs[2 * gb + 1] * s_ga[c + 1] + s_be[c + 1];
-      *reinterpret_cast<uint32_t*>(Xn + row * AB_LD + c) = pack_bf16(a, bb);
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(s_cf + seg * 8), a1 = *reinterpret_cast<const float4*>(s_cf + seg * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(s_cf + C + seg * 8), b1 = *reinterpret_cast<const float4*>(s_cf + C + seg * 8 + 4);
+      const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = warp * 16 + rsub + 4 * k;
+        if (row < T) {
+          const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = pack_bf16(fmaf(__uint_as_float(w[j] << 16), ca[2 * j], cb[2 * j]),
+                             fmaf(__uint_as_float(w[j] & 0xffff0000u), ca[2 * j + 1], cb[2 * j + 1]));
+          *reinterpret_cast<uint4*>(Xn + row * AB_LD + seg * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
     }
-    team_sync();
+    __syncwarp();  // a warp's A fragments come from the 16 rows it has just written itself
 
     // ---- q, k, v projections for this warp's 16 rows (A fragments straight from Xn)
     uint32_t xa[4][4];
@@ -267,13 +300,22 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
       xa[kk][2] = *reinterpret_cast<const uint32_t*>(a0 + 8);
       xa[kk][3] = *reinterpret_cast<const uint32_t*>(a1 + 8);
     }
-    team_sync();  // every warp holds its A fragments: Xn may now be overwritten with the keys (and Xr with the values)
+    // (no barrier: a warp overwrites only its OWN 16 rows of Xn with keys, after it has taken its A fragments from them;
+    //  the previous sample's readers of Ks / Vs were fenced off by the barrier that ends every sample)
+    // acc[16 x 8] = afrag[16 x 64] * W[nb*8 .. nb*8+7][0..63]^T.  W rows are output channels with the 64 inputs contiguous,
+    // i.e. the col-major B operand: one ldmatrix.x4 yields the (b0, b1) fragments of two k-steps (lanes 8m..8m+7
+    // address the rows of the 8x8 block at k = 8m), two of them cover K = 64.
+    const int lm_row = lane & 7, lm_k = (lane >> 3) * 8;
     auto project8 = [&](const uint32_t (&afrag)[4][4], const __nv_bfloat16* W, int nb, float (&acc)[4]) {
       acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
-      const __nv_bfloat16* wr = W + (nb * 8 + g) * AB_LD + 2 * q4;  // B fragment: (k = 2q..2q+1 [+8], n = g)
+      const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(W + (nb * 8 + lm_row) * AB_LD + lm_k));
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        mma_bf16_16816(acc, afrag[kk], *reinterpret_cast<const uint32_t*>(wr + kk * 16), *reinterpret_cast<const uint32_t*>(wr + kk * 16 + 8));
+      for (int h = 0; h < 2; ++h) {
+        uint32_t b[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr + 64 * h));
+        mma_bf16_16816(acc, afrag[2 * h], b[0], b[1]);
+        mma_bf16_16816(acc, afrag[2 * h + 1], b[2], b[3]);
+      }
     };
     uint32_t qa[4][4];
 #pragma unroll
@@ -308,11 +350,7 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
     float s[2 * T16][4];
 #pragma unroll
     for (int nb = 0; nb < 2 * T16; ++nb) {
-      s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.0f;
-      const __nv_bfloat16* kr = Ks + (nb * 8 + g) * AB_LD + 2 * q4;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        mma_bf16_16816(s[nb], qa[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16), *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
+      project8(qa, Ks, nb, s[nb]);  // keys are rows of Ks with the 64 channels contiguous: same operand form as a weight
     }
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
@@ -372,21 +410,26 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
       oa[kk][3] = pack_bf16(o[2 * kk + 1][2] * i1, o[2 * kk + 1][3] * i1);
     }
     __nv_bfloat16* ob = out + static_cast<size_t>(b) * T * C;
+    const int rl0 = g, rl1 = g + 8;  // rows of this warp's private staging tile
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
       float y[4];
       project8(oa, Wp, nb, y);
       const int c = nb * 8 + 2 * q4;
-      if (r0 < T) {
-        const float2 xr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xb + r0 * C + c));  // residual from L2
-        *reinterpret_cast<uint32_t*>(ob + r0 * C + c) = pack_bf16((xr.x + y[0] + s_bp[c]) * out_scale, (xr.y + y[1] + s_bp[c + 1]) * out_scale);
-      }
-      if (r1 < T) {
-        const float2 xr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xb + r1 * C + c));
-        *reinterpret_cast<uint32_t*>(ob + r1 * C + c) = pack_bf16((xr.x + y[2] + s_bp[c]) * out_scale, (xr.y + y[3] + s_bp[c + 1]) * out_scale);
-      }
+      uint32_t* p0 = reinterpret_cast<uint32_t*>(Yst + rl0 * AB_LD + c);
+      uint32_t* p1 = reinterpret_cast<uint32_t*>(Yst + rl1 * AB_LD + c);
+      const float2 x0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p0));  // residual staged on the way in
+      const float2 x1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p1));
+      *p0 = pack_bf16((x0.x + y[0] + s_bp[c]) * out_scale, (x0.y + y[1] + s_bp[c + 1]) * out_scale);
+      *p1 = pack_bf16((x1.x + y[2] + s_bp[c]) * out_scale, (x1.y + y[3] + s_bp[c + 1]) * out_scale);
     }
-    team_sync();  // Xr / Ks / Vs are overwritten by the next sample
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int rl = rsub + 4 * k, row = warp * 16 + rl;
+      if (row < T) *reinterpret_cast<uint4*>(ob + row * C + seg * 8) = *reinterpret_cast<const uint4*>(Yst + rl * AB_LD + seg * 8);
+    }
+    team_sync();  // Xn / Ks / Vs are overwritten by the next sample
   }
 }
 
@@ -399,7 +442,7 @@ int attn_block_launch(const rd_op_attn_block& op, cudaStream_t st) {
   const float scale = 1.0f / sqrtf(static_cast<float>(op.C));
   const int t16 = (op.T + 15) / 16;
   const int tp = 16 * t16;
-  const int smem = (4 * ATT_C * AB_LD + AB_G * 2 * tp * AB_LD) * 2 + (3 * ATT_C + 3 * ATT_C + AB_G * (2 * ATT_C + 2 * op.groups)) * 4 + 64;
+  const int smem = (4 * ATT_C * AB_LD + AB_G * 2 * tp * AB_LD + AB_G * t16 * 16 * AB_LD) * 2 + (3 * ATT_C + 3 * ATT_C + AB_G * (t16 * 2 * ATT_C + 2 * ATT_C)) * 4 + 64;
   const int ctas_per_sm = 227 * 1024 / (smem + 1024) > 4 ? 4 : 227 * 1024 / (smem + 1024);
   int grid = kNumSMs * (ctas_per_sm > 0 ? ctas_per_sm : 1);
   if (grid * AB_G > op.B2) grid = (op.B2 + AB_G - 1) / AB_G;

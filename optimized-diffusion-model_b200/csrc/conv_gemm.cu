@@ -39,7 +39,7 @@ constexpr int CONV_THREADS = 512;
 constexpr int XFORM_THREADS = 320;  // warps 2,3,8..15
 constexpr int EPI_WARPS = 4;        // warps 4..7
 constexpr int MAX_A_STAGES = 3;
-constexpr int MAX_W_STAGES = 4;
+constexpr int MAX_W_STAGES = 12;
 constexpr int MAX_HW = 32;                              // gather maps
 constexpr int STAT_PAIRS = 256;                         // (sample, 8-channel chunk) pairs per statistics batch (streaming mode)
 constexpr int STAT_SCRATCH_BYTES = XFORM_THREADS * 64;  // one 16-float partial record per transform thread
@@ -127,6 +127,12 @@ __device__ __forceinline__ float tanh_approx(float x) {
   do {                                                                                                          \
     if (p.trace && blockIdx.x == 0 && (li) < p.trace_groups) p.trace[((role) * p.trace_groups + (li)) * 8 + (pt)] = clock64(); \
   } while (0)
+
+// Programmatic dependent launch: the next conv launch of the stream may start its prologue (barriers, TMEM, index
+// tables, operand-ring zeroing, filter fetch) on SMs this grid has already left; it must not touch activations
+// before pdl_wait() (= the previous grid has completed and its writes are visible).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void xform_bar() { asm volatile("bar.sync 1, %0;" ::"n"(XFORM_THREADS) : "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   __shared__ uint64_t bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
+  pdl_launch_dependents();
   const ConvSmemLayout L = conv_smem_layout(p);
   unsigned char* As = smem + L.a_off;
   unsigned char* Ws = smem + L.w_off;
@@ -359,15 +366,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               w_lo = w_lo0 + (chunk * ntaps + tap) * w_slab_u;
             } else {
               ws = w_it % w_stages;
-              mbar_wait(&bar_w_full[ws], (w_it / w_stages) & 1);
-              tc_fence_after_sync();
+              if (!(p.debug & 64)) { mbar_wait(&bar_w_full[ws], (w_it / w_stages) & 1); tc_fence_after_sync(); }
               w_lo = w_lo0 + ws * w_slab_u;
             }
             if (leader) {
               if (!skip_mma)
                 issue_tap<NT, TILE_OUTER>(acc, static_cast<uint32_t>(N), a_lo_stage + shift, w_lo, kstep_a, kstep_w, desc_hi, idesc,
                                           (chunk | tcount) != 0);
-              if (!w_resident) {
+              if (!w_resident && !(p.debug & 64)) {
                 if (cl > 1) umma_commit_multicast(&bar_w_empty[ws], cmask); else umma_commit(&bar_w_empty[ws]);
               }
             }
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     __syncwarp();
   } else if (warp == 1) {
     // ================================================================ weight producer (streamed filters only)
-    if (lane == 0 && my_groups > 0 && !p.w_resident) {
+    if (lane == 0 && my_groups > 0 && !p.w_resident && !(p.debug & 64)) {  // debug bit 6: no filter stream at all (timing experiments)
       const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
       const int total = my_groups * p.n_slabs;
       const int tap0 = (p.ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
@@ -443,6 +449,39 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         dst[i] = v * oscale;
       }
     };
+    // Small tables (<= BT_REGS values per thread): the next group's values are requested into registers BEFORE this
+    // group's rows are converted and written to the other half of the table AFTER them, so their L2 / HBM latency is
+    // covered by ~6k cycles of epilogue work instead of sitting on the epilogue's critical path (it was 4k of an 11k
+    // period on the 64-channel 8x9 layers).  Larger tables keep the in-place fill.
+    constexpr int BT_REGS = 12;
+    const bool bt_pref = S * N <= BT_REGS * EPI_WARPS * 32;
+    float btv[BT_REGS];
+    auto bt_load = [&](int g) {
+      const int n = max(0, min(S, p.B2 - g * S)) * N;
+#pragma unroll
+      for (int k = 0; k < BT_REGS; ++k) {
+        const int i = et + k * EPI_WARPS * 32;
+        if (i < n) {
+          const int s = i / N, c = i - s * N;
+          float v = __ldg(p.bias + c);
+          if (p.tproj) {
+            int row = g * S + s;
+            if (p.tproj_wrap > 0 && row > p.tproj_wrap) row = p.tproj_wrap;
+            v += __ldg(p.tproj + static_cast<size_t>(row) * p.tproj_stride + p.tproj_off + c);
+          }
+          btv[k] = v * oscale;
+        }
+      }
+    };
+    auto bt_store = [&](float* dst, int g) {
+      const int n = max(0, min(S, p.B2 - g * S)) * N;
+#pragma unroll
+      for (int k = 0; k < BT_REGS; ++k) {
+        const int i = et + k * EPI_WARPS * 32;
+        if (i < n) dst[i] = btv[k];
+      }
+    };
+    pdl_wait();  // tproj / residual come from earlier launches
     if (my_groups > 0) bt_fill(s_bt, blockIdx.x);
     for (int li = 0; li < my_groups; ++li) {
       const int g = blockIdx.x + li * gridDim.x;
@@ -452,8 +491,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       if (et == 0) RD_TRACE(1, li, 0);
       epi_bar();  // this group's table is complete; the other half is no longer read by anyone
       if (et == 0) RD_TRACE(1, li, 1);
-      // next group's table: its global-load latency hides behind the accumulator wait below
-      if (li + 1 < my_groups) bt_fill(s_bt + ((li + 1) & 1) * S * N, g + gridDim.x);
+      // next group's table
+      const bool more = li + 1 < my_groups;
+      if (more) { if (bt_pref) bt_load(g + gridDim.x); else bt_fill(s_bt + ((li + 1) & 1) * S * N, g + gridDim.x); }
       mbar_wait(&bar_acc_full[buf], (li / p.acc_bufs) & 1);
       tc_fence_after_sync();
       if (et == 0) RD_TRACE(1, li, 2);
@@ -475,6 +515,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+      if (more && bt_pref) bt_store(s_bt + ((li + 1) & 1) * S * N, g + gridDim.x);
       if (et == 0) RD_TRACE(1, li, 3);
     }
   } else {
@@ -495,6 +536,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     }
     xform_bar();
+    pdl_wait();  // the activations read below come from earlier launches
     const size_t gstride0 = static_cast<size_t>(p.S) * p.Hs[0] * p.Ws[0] * p.C[0];
     const size_t gstride1 = static_cast<size_t>(p.S) * p.Hs[1] * p.Ws[1] * p.C[1];
     const float inv_n = GNM != GNM_NONE ? 1.0f / static_cast<float>(p.cpg * P) : 0.0f;
@@ -662,8 +704,41 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           for (int k = 0; k < RC; ++k) raw[k] = nxt[k];
         }
       }
+    } else if (GNM == GNM_NONE) {
+      // ---------------- plain gather (NIN shortcuts, up/down-sampling convs, attention projections): there is nothing
+      // to compute, so the pixels go global -> shared with 16-byte cp.async copies straight into their K-major slots,
+      // one whole 64-channel chunk ahead of the chunk being handed to the tensor core (no registers, ~64 KB in
+      // flight per SM instead of one batch of 8 loads per thread).
+      const int total = my_groups * p.nchunks;
+      auto issue_chunk = [&](int it) {
+        const int li = it / p.nchunks, chunk = it - li * p.nchunks;
+        const int g = blockIdx.x + li * gridDim.x;
+        const int S_act = max(0, min(p.S, p.B2 - g * p.S));
+        const int stage = it % p.a_stages;
+        if (it >= p.a_stages) mbar_wait_relaxed(&bar_a_empty[stage], ((it / p.a_stages) - 1) & 1);
+        if (!(p.debug & 1)) {
+          uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes);
+          const int which = (chunk * 64 < p.C[0]) ? 0 : 1;
+          const __nv_bfloat16* base = (which ? p.src[1] + static_cast<size_t>(g) * gstride1 - p.C[0]
+                                             : p.src[0] + static_cast<size_t>(g) * gstride0) + chunk * 64;
+          const int* toff = t_off + (which ? p.S * P : 0);
+          const int items = S_act * P * 8;
+          for (int item = xt; item < items; item += XFORM_THREADS) {
+            const int sp = item >> 3, kcl = item & 7;
+            cp_async16(a4 + kcl * p.R + t_row[sp], base + toff[sp] + kcl * 8);
+          }
+        }
+        cp_async_commit();
+      };
+      if (total > 0) issue_chunk(0);
+      for (int it = 0; it < total; ++it) {
+        if (it + 1 < total) { issue_chunk(it + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        fence_proxy_async_smem();
+        xform_bar();
+        if (xt == 0) mbar_arrive(&bar_a_full[it % p.a_stages]);
+      }
     } else {
-      // ---------------- streaming mode: optional statistics pass, then a copy/normalise pass per chunk
+      // ---------------- streaming mode: statistics pass, then a normalise pass per chunk
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
         const int S_act = max(0, min(p.S, p.B2 - g * p.S));
@@ -844,6 +919,17 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   const int valid_px = op.H_out * op.W_out;
   double best_score = -1.0;
   ConvParams best = p;
+  static int wmax = -1, astream = 3;
+  static double single_pen = 0.75, tie_eps = 0.0;
+  if (wmax < 0) {
+    const char* e = getenv("RD_CONV_WSTAGES");
+    wmax = e ? atoi(e) : 4;
+    if (wmax < 2) wmax = 2;
+    if (wmax > MAX_W_STAGES) wmax = MAX_W_STAGES;
+    if ((e = getenv("RD_CONV_ASTAGES_STREAM"))) astream = atoi(e) <= 2 ? 2 : 3;
+    if ((e = getenv("RD_CONV_SINGLE_PEN"))) single_pen = atof(e);
+    if ((e = getenv("RD_CONV_TIE_EPS"))) tie_eps = atof(e);  // streamed filters: a larger group wins when within tie_eps
+  }
   for (int nt = 1; nt <= 4; ++nt) {
     if (nt * p.N > 512 || nt * 128 < p.rps) continue;
     ConvParams c = p;
@@ -856,8 +942,13 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     c.a_stages = (p.nchunks == 1) ? 2 : 3;
     c.w_resident = 1;
     if (conv_smem_layout(c).total > smem_cap) {
+      // Streamed filter: the ring has to cover the L2 latency of a slab at the rate the tensor core consumes them
+      // (8-16 KB per ~600 cycles), i.e. tens of KB in flight -- it gets whatever shared memory two operand stages
+      // leave, up to `wmax` slabs.
       c.w_resident = 0;
-      c.w_stages = MAX_W_STAGES;
+      if (c.a_stages > astream) c.a_stages = astream;
+      c.w_stages = wmax < p.n_slabs ? wmax : p.n_slabs;
+      if (c.w_stages < 2) c.w_stages = 2;
       while (c.w_stages > 2 && conv_smem_layout(c).total > smem_cap) --c.w_stages;
       if (conv_smem_layout(c).total > smem_cap && c.a_stages == 3) c.a_stages = 2;
       if (conv_smem_layout(c).total > smem_cap) continue;
@@ -871,9 +962,9 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
       if (slots <= 16) { c.xmode = slots <= 8 ? 8 : 16; c.rc_PS = ps; }
     }
     double score = static_cast<double>(c.S * valid_px) / (nt * 128);
-    if (c.acc_bufs == 1) score *= 0.75;
+    if (c.acc_bufs == 1) score *= (c.w_resident ? 0.75 : single_pen);
     if (!c.w_resident) score *= (nt >= 2 ? 0.97 : 0.85);  // streamed weights are re-read per group: favour larger groups
-    if (score > best_score) { best_score = score; best = c; }
+    if (score > best_score + (c.w_resident ? 0.0 : -tie_eps)) { best_score = score; best = c; }
   }
   RD_REQUIRE(best_score > 0, "conv: no tile geometry fits (Cin=%d N=%d rps=%d)", cin, p.N, p.rps);
   p = best;
@@ -936,13 +1027,20 @@ int conv_launch(const rd_op_conv& op, cudaStream_t st) {
   cfg.blockDim = dim3(CONV_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static int pdl = -1;
+  if (pdl < 0) { const char* ev = getenv("RD_CONV_PDL"); pdl = ev ? atoi(ev) : 1; }  // RD_CONV_PDL=0 restores fully serialised launches (A/B measurements)
+  if (pdl) {
+    attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+    ++cfg.numAttrs;
+  }
   // Streamed filters are re-read by every CTA for every group: keep them persisting in L2 while the (much
   // larger, read-once) activations stream through it.
   static int l2_persist = -1;
@@ -954,13 +1052,13 @@ int conv_launch(const rd_op_conv& op, cudaStream_t st) {
     }
   }
   if (l2_persist && !p.w_resident) {
-    attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
-    attr[1].val.accessPolicyWindow.base_ptr = const_cast<void*>(static_cast<const void*>(p.w));
-    attr[1].val.accessPolicyWindow.num_bytes = static_cast<size_t>(p.n_slabs) * p.w_slab_bytes;
-    attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
-    attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cfg.numAttrs = 2;
+    cudaLaunchAttribute& a = attr[cfg.numAttrs++];
+    a.id = cudaLaunchAttributeAccessPolicyWindow;
+    a.val.accessPolicyWindow.base_ptr = const_cast<void*>(static_cast<const void*>(p.w));
+    a.val.accessPolicyWindow.num_bytes = static_cast<size_t>(p.n_slabs) * p.w_slab_bytes;
+    a.val.accessPolicyWindow.hitRatio = 1.0f;
+    a.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   }
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, p);
   if (e != cudaSuccess) return fail(static_cast<int>(e), "conv_gemm_kernel launch: %s", cudaGetErrorString(e));

@@ -122,6 +122,24 @@ __device__ __forceinline__ float hk_modes(float x, float x0, const float2* __res
   return __fdividef(-2.0f * PI_F * num, fmaf(2.0f, den, 1.0f) + eps);
 }
 
+// M is a compile-time constant for the two cases that cover every converged sum below HK_T_IMAGES (6 and 10
+// images): fully unrolled, image offsets folded into immediates, two independent accumulator chains.
+template <int MC>
+__device__ __forceinline__ float hk_images_fixed(float x, float x0, float c_exp, float scale, float eps) {
+  float numa = 0.0f, numb = 0.0f, dena = 0.0f, denb = 0.0f;
+#pragma unroll
+  for (int m = -MC; m <= MC; ++m) {
+    const float r = static_cast<float>(2 * m);
+    const float da = (r + x) - x0, db = (r - x) - x0;
+    const float ea = ex2_approx(da * da * c_exp), eb = ex2_approx(db * db * c_exp);
+    numa = fmaf(da, ea, numa);
+    numb = fmaf(db, eb, numb);
+    dena += ea;
+    denb += eb;
+  }
+  return __fdividef(scale * (numa - numb), (dena + denb) + eps);
+}
+
 __device__ __forceinline__ float hk_images(float x, float x0, float c_exp, float scale, int M, float eps) {
   float num = 0.0f, den = 0.0f;
   for (int m = -M; m <= M; ++m) {
@@ -214,8 +232,16 @@ __global__ void __launch_bounds__(256) score_hk_kernel(const float* __restrict__
       for (int v = 0; v < VEC; ++v) r[v] = hk_modes(xv[v], x0v[v], e_tab[s], cnt, eps);
     } else {
       const float ce = tab.c_exp[s], sc = tab.scale[s];
+      if (cnt == 1) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) r[v] = hk_images(xv[v], x0v[v], ce, sc, cnt, eps);
+        for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<1>(xv[v], x0v[v], ce, sc, eps);
+      } else if (cnt == 2) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<2>(xv[v], x0v[v], ce, sc, eps);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = hk_images(xv[v], x0v[v], ce, sc, cnt, eps);
+      }
     }
     if (VEC == 4) {
       st_stream4(out + off, make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]));
@@ -322,6 +348,65 @@ __global__ void __launch_bounds__(32 * PC_SPB) pc_norms_kernel(const float* __re
     acc_g += sqrtf(g2);
     acc_n += sqrtf(n2);
   }
+  if (lane == 0) { sg[warp] = acc_g; sn[warp] = acc_n; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.0f, c = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PC_SPB; ++i) { a += sg[i]; c += sn[i]; }
+    partial[2 * blockIdx.x] = a;
+    partial[2 * blockIdx.x + 1] = c;
+  }
+}
+
+// Large batches (D % 4 == 0): one warp per sample leaves 14 of 32 lanes idle at D = 72 (18 quads), and the kernel is
+// bound by the Philox / Box-Muller arithmetic, not by its 4 B/element of traffic.  Here a warp takes PCB_SC samples at
+// a time, walks their quads with all 32 lanes, parks the per-quad sums of squares in shared memory and lets one
+// lane per sample add them in a fixed order.
+constexpr int PCB_SC = 16;
+constexpr int PCB_MAXQ = 32;  // D <= 128
+
+__global__ void __launch_bounds__(32 * PC_SPB) pc_norms_batched_kernel(const float* __restrict__ grad,
+                                                                       const float* __restrict__ noise,
+                                                                       float* __restrict__ partial, size_t B, int Q,
+                                                                       uint64_t seed, uint32_t draw_base,
+                                                                       const int32_t* __restrict__ step_ctr,
+                                                                       size_t noise_step_stride) {
+  __shared__ float2 part[PC_SPB][PCB_SC * PCB_MAXQ];
+  __shared__ float sg[PC_SPB], sn[PC_SPB];
+  if (noise && step_ctr) noise += static_cast<size_t>(*step_ctr) * noise_step_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t draw = draw_index(draw_base, step_ctr, 0);
+  float acc_g = 0.0f, acc_n = 0.0f;
+  const size_t nchunks = (B + PCB_SC - 1) / PCB_SC;
+  for (size_t ch = static_cast<size_t>(blockIdx.x) * PC_SPB + warp; ch < nchunks; ch += static_cast<size_t>(gridDim.x) * PC_SPB) {
+    const size_t b0 = ch * PCB_SC;
+    const int ns = static_cast<int>(min(static_cast<size_t>(PCB_SC), B - b0));
+    const size_t q0 = b0 * Q;
+    for (int it = lane; it < ns * Q; it += 32) {
+      const size_t q = q0 + it;
+      const float4 g = *reinterpret_cast<const float4*>(grad + 4 * q);
+      float z[4];
+      if (noise) {
+        const float4 nz = *reinterpret_cast<const float4*>(noise + 4 * q);
+        z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
+      } else {
+        philox_normal4(seed, draw, q, z);
+      }
+      part[warp][it] = make_float2(g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w,
+                                   z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3]);
+    }
+    __syncwarp();
+    if (lane < ns) {
+      float g2 = 0.0f, n2 = 0.0f;
+      for (int k = 0; k < Q; ++k) { const float2 v = part[warp][lane * Q + k]; g2 += v.x; n2 += v.y; }
+      acc_g += sqrtf(g2);
+      acc_n += sqrtf(n2);
+    }
+    __syncwarp();
+  }
+  acc_g = warp_sum(acc_g);
+  acc_n = warp_sum(acc_n);
   if (lane == 0) { sg[warp] = acc_g; sn[warp] = acc_n; }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -554,6 +639,14 @@ int rd_pc_norms(const float* grad, const float* noise, float* partial, int* nblk
                 void* stream) {
   RD_REQUIRE(grad && partial && B > 0 && D > 0, "rd_pc_norms: bad arguments");
   size_t want = (B + PC_SPB - 1) / PC_SPB, cap = static_cast<size_t>(kNumSMs) * 8;
+  if (D % 4 == 0 && D / 4 <= PCB_MAXQ && B >= cap * PC_SPB * PCB_SC && all_aligned16(grad, noise, nullptr, nullptr) &&
+      (!noise || noise_step_stride % 4 == 0)) {
+    // enough samples to give every warp of a full grid whole chunks of PCB_SC samples
+    if (nblk) *nblk = static_cast<int>(cap);
+    pc_norms_batched_kernel<<<static_cast<int>(cap), 32 * PC_SPB, 0, static_cast<cudaStream_t>(stream)>>>(
+        grad, noise, partial, B, static_cast<int>(D / 4), seed, draw_base, step_ctr, noise_step_stride);
+    return check_launch("pc_norms_batched_kernel");
+  }
   int blocks = static_cast<int>(want < cap ? want : cap);
   if (nblk) *nblk = blocks;
   pc_norms_kernel<<<blocks, 32 * PC_SPB, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -106,8 +106,7 @@ int rd_sampler_create(const rd_sampler_desc* d, rd_sampler** out) {
   RD_REQUIRE(d && out, "rd_sampler_create: null argument");
   RD_REQUIRE(d->forward && d->x && d->score && d->partial && d->g_table && d->step_ctr, "rd_sampler_create: null pointer");
   RD_REQUIRE(d->B > 0 && d->D > 0 && d->n_corrector_steps >= 0, "rd_sampler_create: bad sizes");
-  RD_REQUIRE(d->noise_tape || ((static_cast<size_t>(d->B) * d->D) % 4 == 0 && d->D % 4 == 0),
-             "rd_sampler_create: in-kernel Philox noise needs D %% 4 == 0");
+  // (any D: Philox quads are indexed over the flat tensor, ragged ends are masked in the kernels)
   rd_sampler* s = new (std::nothrow) rd_sampler();
   RD_REQUIRE(s, "rd_sampler_create: out of memory");
   s->d = *d;

@@ -150,3 +150,24 @@ def test_philox_stream():
     c, _, _ = ops.corrector_step(x, s, None, 0.16, seed=99)
     d, _, _ = ops.corrector_step(x, s, tape0, 0.16)
     assert torch.equal(c, d)
+
+
+def test_corrector_large_batch_paths():
+    """Batches large enough for the all-lanes norm kernel (>= 151552 samples) and the bounded partial table: the batch
+    means match torch, and in-kernel Philox noise still equals the dumped tape bit for bit."""
+    g = torch.Generator(device=DEV).manual_seed(8)
+    B = 1 << 18
+    x = torch.rand((B, 1, 8, 9), device=DEV, generator=g)
+    s = torch.randn((B, 1, 8, 9), device=DEV, generator=g) * 3
+    z = torch.randn((B, 1, 8, 9), device=DEV, generator=g)
+    xc, xcm, stats = ops.corrector_step(x, s, z, 0.16)
+    gn = s.flatten(1).double().norm(dim=1).mean()
+    nn = z.flatten(1).double().norm(dim=1).mean()
+    assert float(stats[0]) == pytest.approx(float(gn), rel=2e-6) and float(stats[1]) == pytest.approx(float(nn), rel=2e-6)
+    step = (0.16 * nn / gn) ** 2 * 2
+    want = cube.reflect((x.double() + step * s.double() + torch.sqrt(step * 2) * z.double()).float())
+    assert float((xc - want).abs().max()) <= 2e-5 and bool(cube.inside(xc).all()) and bool(cube.inside(xcm).all())
+    tape0 = ops.philox_normal(x.shape, 99, 0, DEV)
+    c, _, st_c = ops.corrector_step(x, s, None, 0.16, seed=99)
+    d, _, st_d = ops.corrector_step(x, s, tape0, 0.16)
+    assert torch.equal(c, d) and torch.equal(st_c, st_d)

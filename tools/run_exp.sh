@@ -1,0 +1,6 @@
+#!/bin/bash
+# geometry / ablation experiments: per-op table of one guided forward under different knobs
+mkdir -p gpurun_out
+run() { name=$1; shift; env "$@" timeout 200 python tools/gpu_optime.py > gpurun_out/optime_$name.log 2>&1; echo "== $name: $(sed -n 1,3p gpurun_out/optime_$name.log | tr '\n' ' ')"; }
+run base RD_X=0
+run pdl RD_CONV_PDL=1
