@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=128)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c2", action="store_true", help="skip the reflect / score_hk / fused-update HBM microbench")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -270,6 +271,7 @@ def main():
         t = torch.tensor([ms_total, ag_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ag_ms = float(t[0]), float(t[1])
+    launches_per_iter = eng.launches_per_iter()
     ms_per_step = ms_total / K
     pass_s = (ITERS_PER_PASS * ms_per_step + ag_ms) / 1e3
     value = world * B / pass_s
@@ -333,6 +335,26 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- the HBM-bound kernels of the path (BASELINE config C2 shape, [2^20,1,8,9]): achieved GB/s of algorithmic
+    # bytes against the measured copy bandwidth, timed live with CUDA events (tools/bench_c2.py)
+    hbm = None
+    if not args.no_c2:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_c2
+            warm = torch.rand((1 << 24,), device=dev)
+            for _ in range(50):   # the CPU-side bookkeeping above leaves the GPU idle; bring clocks back up first
+                warm.mul_(1.0001)
+            torch.cuda.synchronize(dev)
+            del warm
+            rows = bench_c2.run(types.SimpleNamespace(log2B=20, reps=10, only=None, out=None), dev=dev, quiet=True)
+            hbm = [{"kernel": r["case"], "ms": round(r["ms_avg"], 4), "GBps": round(r["GBps"], 1), "frac": round(r["frac"], 4)}
+                   for r in rows if r["case"] in ("reflect", "score_hk sigma=0.1", "score_hk sigma~logU[0.01,5]",
+                                                  "predictor step (x,score in; x out; Philox)",
+                                                  "corrector norms (grad in; Philox)", "corrector apply (x,grad in; x out; Philox)")]
+        except Exception as e:  # the headline line must not depend on the side measurement
+            hbm = [{"error": repr(e)}]
+
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -351,8 +373,9 @@ def main():
                        "l2": "activations of one iteration (>5 GB at 2B=16384) exceed the 126 MB L2; no flush needed",
                        "noise": "in-kernel Philox", "cuda_graph": True, "all_gather_ms": ag_ms,
                        "all_samples_inside_cube": inside, "parallelism": f"batch-sharded x{world}, no collective in the loop"},
-            "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": eng.launches_per_iter() * K}
+            "clocks": clk, "roofline": roof, "hbm_kernels": {"shape": "[2^20,1,8,9] fp32 (C2)", "peak_GBps": pk["hbm_gbs"],
+                                                              "peak_source": pk["source"], "rows": hbm},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_iter * K}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -69,6 +69,7 @@ struct ConvParams {
   int w_resident, w_stages, w_slab_bytes, n_slabs;
   int acc_bufs;
   int n_issuers;     // MMA-issuing warps (tiles are dealt round-robin)
+  int w_reps;        // identical copies of the packed filter, n_slabs*w_slab_bytes apart; CTA i reads copy i % w_reps
   int cluster;       // CTAs per thread-block cluster sharing the streamed filter by TMA multicast (1 = no cluster)
   int xmode, rc_PS;  // transform mode: >0 = register-cached single pass (value = register slots, rc_PS pixel slices), 0 = streaming
   int gnm;
@@ -331,7 +332,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     const int tap0 = (w_resident || ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
     if (w_resident && my_groups > 0) {
       if (leader) {  // the resident filter is fetched once per CTA
-        const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
+        const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w) +
+                                  static_cast<size_t>(blockIdx.x % p.w_reps) * p.n_slabs * p.w_slab_bytes;
         mbar_arrive_expect_tx(&bar_w_full[0], p.n_slabs * p.w_slab_bytes);
         for (int sidx = 0; sidx < p.n_slabs; ++sidx)
           bulk_g2s(Ws + sidx * p.w_slab_bytes, wg + static_cast<size_t>(sidx) * p.w_slab_bytes, p.w_slab_bytes, &bar_w_full[0]);
@@ -406,7 +408,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   } else if (warp == 1) {
     // ================================================================ weight producer (streamed filters only)
     if (lane == 0 && my_groups > 0 && !p.w_resident && !(p.debug & 64)) {  // debug bit 6: no filter stream at all (timing experiments)
-      const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
+      const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w) +
+                                static_cast<size_t>((blockIdx.x / p.cluster) % p.w_reps) * p.n_slabs * p.w_slab_bytes;
       const int total = my_groups * p.n_slabs;
       const int tap0 = (p.ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
       for (int it = 0; it < total; ++it) {
@@ -971,6 +974,11 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   p.n_groups = (op.B2 + p.S - 1) / p.S;
   p.n_issuers = 1;
   p.cluster = 1;
+  {
+    static int reps = -1;
+    if (reps < 0) { const char* e = getenv("RD_CONV_WREPS"); reps = e ? atoi(e) : 1; if (reps < 1) reps = 1; if (reps > 16) reps = 16; }
+    p.w_reps = reps;  // rdb200/pack.py stores that many copies of every filter
+  }
   if (!p.w_resident) {
     static int want = -1;
     // EXPERIMENTAL, opt-in: measured no gain on B200 (the filter stream is latency-, not bandwidth-bound) and the
@@ -1055,7 +1063,7 @@ int conv_launch(const rd_op_conv& op, cudaStream_t st) {
     cudaLaunchAttribute& a = attr[cfg.numAttrs++];
     a.id = cudaLaunchAttributeAccessPolicyWindow;
     a.val.accessPolicyWindow.base_ptr = const_cast<void*>(static_cast<const void*>(p.w));
-    a.val.accessPolicyWindow.num_bytes = static_cast<size_t>(p.n_slabs) * p.w_slab_bytes;
+    a.val.accessPolicyWindow.num_bytes = static_cast<size_t>(p.n_slabs) * p.w_slab_bytes * p.w_reps;
     a.val.accessPolicyWindow.hitRatio = 1.0f;
     a.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     a.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;

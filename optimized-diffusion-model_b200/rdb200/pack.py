@@ -36,6 +36,12 @@ def pad_rows(w: torch.Tensor, ld: int) -> torch.Tensor:
     return out
 
 
+def conv_weight_replicas() -> int:
+    """Copies of every packed conv filter (must match RD_CONV_WREPS as read by csrc/conv_gemm.cu)."""
+    import os
+    return max(1, min(16, int(os.environ.get("RD_CONV_WREPS", "1"))))
+
+
 class PackedWeights:
     """Device-resident packed parameters of one NCSNpp instance."""
 
@@ -47,6 +53,10 @@ class PackedWeights:
 
     def _put(self, name: str, value: torch.Tensor):
         value = value.detach().to(self.device)
+        if name.endswith(".w") and conv_weight_replicas() > 1:
+            # streamed filters: identical copies at distinct addresses, CTA i reads copy i % R (conv_gemm.cu), which
+            # spreads the 148 CTAs' simultaneous requests for one slab over R times as many L2 lines
+            value = value.unsqueeze(0).repeat((conv_weight_replicas(),) + (1,) * value.dim())
         if name in self.t:
             if self.t[name].shape != value.shape or self.t[name].dtype != value.dtype:
                 raise RuntimeError(f"packed tensor {name} changed shape/dtype; rebuild the engine")

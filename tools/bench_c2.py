@@ -52,8 +52,13 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default=None, help="substring filter on the case name (for ncu captures)")
     args = ap.parse_args()
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
+    torch.cuda.set_device(0)
+    run(args)
+
+
+def run(args, dev=None, quiet=False):
+    """-> list of result dicts (one per case); `args` needs .log2B .reps .only .out"""
+    dev = dev or torch.device("cuda", torch.cuda.current_device())
     B, D = 1 << args.log2B, 72
     n = B * D
     peak, src = hbm_peak()
@@ -73,7 +78,8 @@ def main():
         if extra:
             line.update(extra)
         lines.append(line)
-        print(json.dumps(line), flush=True)
+        if not quiet:
+            print(json.dumps(line), flush=True)
 
     def want(name):
         return args.only is None or args.only in name
@@ -120,6 +126,7 @@ def main():
         with open(args.out, "w") as f:
             for ln in lines:
                 f.write(json.dumps(ln) + "\n")
+    return lines
 
 
 if __name__ == "__main__":

@@ -18,3 +18,5 @@ timeout 200 python tools/prof_target.py > gpurun_out/prof_plain3.log 2>&1 && \
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_gemm -c 96 --csv --log-file gpurun_out/conv_traffic.csv python tools/prof_target.py > gpurun_out/ncu_traffic.log 2>&1
 echo "ncu traffic rc=$?"
 fi
+# BASELINE config C2: HBM-bound kernels (timings without a profiler, then one full capture per kernel)
+bash tools/run_c2.sh
