@@ -452,38 +452,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         dst[i] = v * oscale;
       }
     };
-    // Small tables (<= BT_REGS values per thread): the next group's values are requested into registers BEFORE this
-    // group's rows are converted and written to the other half of the table AFTER them, so their L2 / HBM latency is
-    // covered by ~6k cycles of epilogue work instead of sitting on the epilogue's critical path (it was 4k of an 11k
-    // period on the 64-channel 8x9 layers).  Larger tables keep the in-place fill.
-    constexpr int BT_REGS = 12;
-    const bool bt_pref = S * N <= BT_REGS * EPI_WARPS * 32;
-    float btv[BT_REGS];
-    auto bt_load = [&](int g) {
-      const int n = max(0, min(S, p.B2 - g * S)) * N;
-#pragma unroll
-      for (int k = 0; k < BT_REGS; ++k) {
-        const int i = et + k * EPI_WARPS * 32;
-        if (i < n) {
-          const int s = i / N, c = i - s * N;
-          float v = __ldg(p.bias + c);
-          if (p.tproj) {
-            int row = g * S + s;
-            if (p.tproj_wrap > 0 && row > p.tproj_wrap) row = p.tproj_wrap;
-            v += __ldg(p.tproj + static_cast<size_t>(row) * p.tproj_stride + p.tproj_off + c);
-          }
-          btv[k] = v * oscale;
-        }
-      }
-    };
-    auto bt_store = [&](float* dst, int g) {
-      const int n = max(0, min(S, p.B2 - g * S)) * N;
-#pragma unroll
-      for (int k = 0; k < BT_REGS; ++k) {
-        const int i = et + k * EPI_WARPS * 32;
-        if (i < n) dst[i] = btv[k];
-      }
-    };
     pdl_wait();  // tproj / residual come from earlier launches
     if (my_groups > 0) bt_fill(s_bt, blockIdx.x);
     for (int li = 0; li < my_groups; ++li) {
@@ -494,9 +462,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       if (et == 0) RD_TRACE(1, li, 0);
       epi_bar();  // this group's table is complete; the other half is no longer read by anyone
       if (et == 0) RD_TRACE(1, li, 1);
-      // next group's table
-      const bool more = li + 1 < my_groups;
-      if (more) { if (bt_pref) bt_load(g + gridDim.x); else bt_fill(s_bt + ((li + 1) & 1) * S * N, g + gridDim.x); }
+      // next group's table: its global-load latency hides behind the accumulator wait below.  (Requesting it into
+      // registers before the rows and storing it after them was measured slower: +1.5 % conv time from the extra
+      // register pressure in this 128-register role.)
+      if (li + 1 < my_groups) bt_fill(s_bt + ((li + 1) & 1) * S * N, g + gridDim.x);
       mbar_wait(&bar_acc_full[buf], (li / p.acc_bufs) & 1);
       tc_fence_after_sync();
       if (et == 0) RD_TRACE(1, li, 2);
@@ -518,7 +487,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
-      if (more && bt_pref) bt_store(s_bt + ((li + 1) & 1) * S * N, g + gridDim.x);
       if (et == 0) RD_TRACE(1, li, 3);
     }
   } else {

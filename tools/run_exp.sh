@@ -1,6 +1,7 @@
 #!/bin/bash
-# geometry / ablation experiments: per-op table of one guided forward under different knobs
 mkdir -p gpurun_out
 run() { name=$1; shift; env "$@" timeout 200 python tools/gpu_optime.py > gpurun_out/optime_$name.log 2>&1; echo "== $name: $(sed -n 1,3p gpurun_out/optime_$name.log | tr '\n' ' ')"; }
 run base RD_X=0
-run pdl RD_CONV_PDL=1
+run nobt RD_CONV_DEBUG=128
+run base2 RD_X=0
+run nobt2 RD_CONV_DEBUG=128
