@@ -321,7 +321,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     const int N = p.N, ntaps = p.ntaps, nchunks = p.nchunks, Wp = p.Wp;
     const int a_stages = p.a_stages, w_stages = p.w_stages, acc_bufs = p.acc_bufs;
     const bool w_resident = p.w_resident != 0, skip_mma = (p.debug & 4) != 0;
-    const int cl = p.cluster;
     const uint32_t idesc = umma_idesc_bf16(128, N);
     const uint64_t desc_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
     const uint32_t a_lo0 = (smem_u32(As) >> 4) | (static_cast<uint32_t>(p.R) << 16);  // LBO = R*16 B
@@ -329,7 +328,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     const uint32_t a_stage_u = p.a_stage_bytes >> 4, w_slab_u = p.w_slab_bytes >> 4;
     const uint32_t kstep_a = 2 * p.R, kstep_w = 2 * N;
     const uint32_t acc_stride = p.n_tiles * N;
-    const int tap0 = (w_resident || ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
     if (w_resident && my_groups > 0) {
       if (leader) {  // the resident filter is fetched once per CTA
         const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w) +
@@ -341,50 +339,55 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       mbar_wait(&bar_w_full[0], 0);
       tc_fence_after_sync();
     }
-    auto run = [&](auto nt_c, auto outer_c) {
+    // The tap loop is unrolled at compile time (NTAPS = 9 or 1), the streamed and the resident filter get their own
+    // copies of it, and nothing in it is looked up or divided: for N = 128 a tap is only eight MMAs (~540 cycles of
+    // tensor-core work), and the ~130 scalar instructions per tap of the generic loop (ring index arithmetic, tap
+    // rotation, debug / cluster branches, register->uniform moves) kept the single issuing thread BEHIND the tensor
+    // core -- 102 cycles per MMA issued against 67 executed (tools/probe_umma2.cu order 12).
+    const bool no_stream = (p.debug & 64) != 0;
+    auto run = [&](auto nt_c, auto outer_c, auto taps_c) {
       constexpr int NT = decltype(nt_c)::value;
       constexpr bool TILE_OUTER = decltype(outer_c)::value;
-      int a_it = 0, w_it = 0;
+      constexpr int NTAPS = decltype(taps_c)::value;
+      int a_stage_i = 0, a_par = 0, ws = 0, w_par = 0;
+      const uint32_t uN = static_cast<uint32_t>(N), uWp = static_cast<uint32_t>(Wp);
       for (int li = 0; li < my_groups; ++li) {
         const int buf = li % acc_bufs, useb = li / acc_bufs;
         if (leader) RD_TRACE(0, li, 0);
         if (useb > 0) { mbar_wait(&bar_acc_empty[buf], (useb - 1) & 1); tc_fence_after_sync(); }
         if (leader) RD_TRACE(0, li, 1);
         const uint32_t acc = tmem + buf * acc_stride;
-        for (int chunk = 0; chunk < nchunks; ++chunk, ++a_it) {
-          const int stage = a_it % a_stages;
-          mbar_wait(&bar_a_full[stage], (a_it / a_stages) & 1);
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+          const int stage = a_stage_i;
+          mbar_wait(&bar_a_full[stage], a_par);
           tc_fence_after_sync();
           if (chunk == 0 && leader) RD_TRACE(0, li, 2);
           const uint32_t a_lo_stage = a_lo0 + stage * a_stage_u;
-          // Streamed filters: every CTA walks the taps of a chunk in its own rotation, so that the 148 CTAs do
-          // not all pull the same 16 KB slab out of the same L2 slices at the same moment.
-          int tap = tap0;
-          int shift = (ntaps == 9) ? (tap / 3) * Wp + (tap % 3) : 0, col = tap % 3;
-          for (int tcount = 0; tcount < ntaps; ++tcount) {
-            uint32_t w_lo;
-            int ws = 0;
-            if (w_resident) {
-              w_lo = w_lo0 + (chunk * ntaps + tap) * w_slab_u;
-            } else {
-              ws = w_it % w_stages;
-              if (!(p.debug & 64)) { mbar_wait(&bar_w_full[ws], (w_it / w_stages) & 1); tc_fence_after_sync(); }
-              w_lo = w_lo0 + ws * w_slab_u;
+          if (w_resident) {
+            const uint32_t w_chunk = w_lo0 + chunk * NTAPS * w_slab_u;
+#pragma unroll
+            for (int t = 0; t < NTAPS; ++t) {
+              const uint32_t shift = NTAPS == 9 ? (t / 3) * uWp + (t % 3) : 0u;  // tap (dy,dx) -> row shift dy*Wp + dx
+              if (leader && !skip_mma)
+                issue_tap<NT, TILE_OUTER>(acc, uN, a_lo_stage + shift, w_chunk + t * w_slab_u, kstep_a, kstep_w, desc_hi, idesc,
+                                          (chunk | t) != 0);
             }
-            if (leader) {
-              if (!skip_mma)
-                issue_tap<NT, TILE_OUTER>(acc, static_cast<uint32_t>(N), a_lo_stage + shift, w_lo, kstep_a, kstep_w, desc_hi, idesc,
-                                          (chunk | tcount) != 0);
-              if (!w_resident && !(p.debug & 64)) {
-                if (cl > 1) umma_commit_multicast(&bar_w_empty[ws], cmask); else umma_commit(&bar_w_empty[ws]);
+          } else {
+#pragma unroll
+            for (int t = 0; t < NTAPS; ++t) {
+              const uint32_t shift = NTAPS == 9 ? (t / 3) * uWp + (t % 3) : 0u;
+              if (!no_stream) { mbar_wait(&bar_w_full[ws], w_par); tc_fence_after_sync(); }
+              if (leader) {
+                if (!skip_mma)
+                  issue_tap<NT, TILE_OUTER>(acc, uN, a_lo_stage + shift, w_lo0 + ws * w_slab_u, kstep_a, kstep_w, desc_hi, idesc,
+                                            (chunk | t) != 0);
+                if (!no_stream) umma_commit(&bar_w_empty[ws]);
               }
+              if (++ws == w_stages) { ws = 0; w_par ^= 1; }
             }
-            if (!w_resident) ++w_it;
-            // next tap: (dy,dx) -> row shift dy*Wp + dx, wrapping around after the last tap
-            if (++tap == ntaps) { tap = 0; col = 0; shift = 0; }
-            else if (++col == 3) { col = 0; shift += Wp - 2; } else { shift += 1; }
           }
           if (leader) umma_commit(&bar_a_empty[stage]);  // operand stage reusable once these MMAs have read it
+          if (++a_stage_i == a_stages) { a_stage_i = 0; a_par ^= 1; }
         }
         if (leader) {
           umma_commit(&bar_acc_full[buf]);
@@ -393,16 +396,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     };
     using std::integral_constant;
+    auto run_taps = [&](auto nt_c, auto outer_c) {
+      if (ntaps == 9) run(nt_c, outer_c, integral_constant<int, 9>{});
+      else run(nt_c, outer_c, integral_constant<int, 1>{});
+    };
     const int sel = (N <= 64 ? 0 : 4) + p.n_tiles - 1;  // narrow N: tiles of a k-step together; N >= 128: tile-outer
     switch (sel) {
-      case 0: run(integral_constant<int, 1>{}, integral_constant<bool, false>{}); break;
-      case 1: run(integral_constant<int, 2>{}, integral_constant<bool, false>{}); break;
-      case 2: run(integral_constant<int, 3>{}, integral_constant<bool, false>{}); break;
-      case 3: run(integral_constant<int, 4>{}, integral_constant<bool, false>{}); break;
-      case 4: run(integral_constant<int, 1>{}, integral_constant<bool, true>{}); break;
-      case 5: run(integral_constant<int, 2>{}, integral_constant<bool, true>{}); break;
-      case 6: run(integral_constant<int, 3>{}, integral_constant<bool, true>{}); break;
-      default: run(integral_constant<int, 4>{}, integral_constant<bool, true>{}); break;
+      case 0: run_taps(integral_constant<int, 1>{}, integral_constant<bool, false>{}); break;
+      case 1: run_taps(integral_constant<int, 2>{}, integral_constant<bool, false>{}); break;
+      case 2: run_taps(integral_constant<int, 3>{}, integral_constant<bool, false>{}); break;
+      case 3: run_taps(integral_constant<int, 4>{}, integral_constant<bool, false>{}); break;
+      case 4: run_taps(integral_constant<int, 1>{}, integral_constant<bool, true>{}); break;
+      case 5: run_taps(integral_constant<int, 2>{}, integral_constant<bool, true>{}); break;
+      case 6: run_taps(integral_constant<int, 3>{}, integral_constant<bool, true>{}); break;
+      default: run_taps(integral_constant<int, 4>{}, integral_constant<bool, true>{}); break;
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -411,14 +418,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w) +
                                 static_cast<size_t>((blockIdx.x / p.cluster) % p.w_reps) * p.n_slabs * p.w_slab_bytes;
       const int total = my_groups * p.n_slabs;
-      const int tap0 = (p.ntaps != 9) ? 0 : static_cast<int>((blockIdx.x / p.cluster) % 9);
+      const int tap0 = 0;  // natural tap order (a per-CTA rotation against L2 hot spots was measured to change nothing)
+      const int w_stages = p.w_stages, ntaps = p.ntaps, nchunks = p.nchunks;
+      // (slot, parity) and (chunk, tap) are counters, not `%` / `/` of the iteration index: this single thread has to
+      // turn a slab around in well under the ~500 cycles the tensor core needs to consume one
+      int ws = 0, e_par = 1, chunk = 0, k = 0, tap = tap0;
       for (int it = 0; it < total; ++it) {
-        const int ws = it % p.w_stages;
-        if (it >= p.w_stages) mbar_wait(&bar_w_empty[ws], ((it / p.w_stages) - 1) & 1);
+        if (it >= w_stages) mbar_wait(&bar_w_empty[ws], e_par);
         mbar_arrive_expect_tx(&bar_w_full[ws], p.w_slab_bytes);
-        const int sl = it % p.n_slabs;  // position in this CTA's (rotated) order -> actual slab
-        const int chunk = sl / p.ntaps, tap = (sl - chunk * p.ntaps + tap0) % p.ntaps;
-        const unsigned char* src = wg + static_cast<size_t>(chunk * p.ntaps + tap) * p.w_slab_bytes;
+        const unsigned char* src = wg + static_cast<size_t>(chunk * ntaps + tap) * p.w_slab_bytes;
         if (p.cluster > 1) {
           // every CTA of the cluster fetches 1/cluster of the slab and multicasts it to all of them
           const uint32_t part = p.w_slab_bytes / p.cluster;
@@ -426,6 +434,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         } else {
           bulk_g2s(Ws + ws * p.w_slab_bytes, src, p.w_slab_bytes, &bar_w_full[ws]);
         }
+        if (++ws == w_stages) { ws = 0; e_par ^= 1; }   // first wait on a slot (round 1) uses parity 0
+        if (++tap == ntaps) tap = 0;                      // this CTA's rotated tap order
+        if (++k == ntaps) { k = 0; tap = tap0; if (++chunk == nchunks) chunk = 0; }
       }
     }
     __syncwarp();
@@ -947,13 +958,9 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     if (reps < 0) { const char* e = getenv("RD_CONV_WREPS"); reps = e ? atoi(e) : 1; if (reps < 1) reps = 1; if (reps > 16) reps = 16; }
     p.w_reps = reps;  // rdb200/pack.py stores that many copies of every filter
   }
-  if (!p.w_resident) {
-    static int want = -1;
-    // EXPERIMENTAL, opt-in: measured no gain on B200 (the filter stream is latency-, not bandwidth-bound) and the
-    // 2-CTA variant does not yet pass the parity tests; kept as groundwork, never enabled by default.
-    if (want < 0) { const char* e = getenv("RD_CONV_CLUSTER"); want = e ? atoi(e) : 1; }
-    if ((want == 2 || want == 4) && p.w_slab_bytes % (16 * want) == 0) p.cluster = want;
-  }
+  // (thread-block clusters sharing the streamed filter by TMA multicast were built and measured in round 1: no gain for
+  //  2 CTAs, a loss for 4 -- the stream was never L2-bound, see DESIGN.md -- and the issue loop no longer carries the
+  //  multicast commit, so launches are always un-clustered)
   p.tmem_cols = next_pow2_cols(p.acc_bufs * p.n_tiles * p.N);
   smem_bytes = conv_smem_layout(p).total;
   const int sms = conv_num_sms();

@@ -71,6 +71,41 @@ __global__ void __launch_bounds__(512) probe2(const __nv_bfloat16* __restrict__ 
               const uint64_t db = umma_desc_kmajor(smem_u32(Bs) + ((kk * 2) * N) * 16, N * 16, 128);
               umma_bf16_ss(tmem + tile * N, da, db, idesc, kk > 0);
             }
+        } else if (order >= 10 && order <= 13) {
+          // accumulator-residency experiments (N >= 128): every MMA accumulates (as in the conv kernel after the first tap)
+          //   10: tile-outer, 4-MMA chains per tile (the conv kernel's order), one B slab
+          //   12: for tap: for tile: 4 k-steps   (conv kernel: a tile switch every 4 MMAs, B per tap)
+          //   13: for tile: for tap: 4 k-steps   (36-MMA chains, all nine slabs resident)
+          //   11: for tap pair: for tile: 2 x 4 k-steps (8-MMA chains, two slabs at a time)
+          if (order == 10) {
+            for (int tile = 0; tile < ntiles; ++tile)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t da = umma_desc_kmajor(smem_u32(As) + ((kk * 2) * R + tile * 128 + shift) * 16, R * 16, 128);
+                const uint64_t db = umma_desc_kmajor(smem_u32(Bs) + ((kk * 2) * N) * 16, N * 16, 128);
+                umma_bf16_ss(tmem + tile * N, da, db, idesc, 1);
+              }
+          } else if (order == 12 || order == 13 || order == 11) {
+            const int outer = order == 13 ? ntiles : (order == 11 ? 5 : 9);
+            for (int o = 0; o < outer; ++o) {
+              const int inner = order == 13 ? 9 : ntiles;
+              for (int in = 0; in < inner; ++in) {
+                const int tile = order == 13 ? o : in;
+                const int tap_lo = order == 13 ? in : (order == 11 ? 2 * o : o);
+                const int ntap = (order == 11 && tap_lo + 1 < 9) ? 2 : 1;
+                for (int tt = 0; tt < ntap; ++tt) {
+                  const int tap = tap_lo + tt;
+                  const int sh = (tap / 3) * 8 + tap % 3;
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t da = umma_desc_kmajor(smem_u32(As) + ((kk * 2) * R + tile * 128 + sh) * 16, R * 16, 128);
+                    const uint64_t db = umma_desc_kmajor(smem_u32(Bs) + tap * N * 128 + ((kk * 2) * N) * 16, N * 16, 128);
+                    umma_bf16_ss(tmem + tile * N, da, db, idesc, 1);
+                  }
+                }
+              }
+            }
+          }
         } else if (order == 1) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
@@ -297,6 +332,6 @@ int main(int argc, char** argv) {
       }
     }
   printf("PROBE2 off=%d rnd=%d layout=%d N=%d shift=%d tiles=%d order=%d noise=%d grid=%d mismatches=%d cycles/MMA=%.1f noise_cycles/iter=%lld\n", argc > 10 ? atoi(argv[10]) : 0, rnd, layout, N, shift, ntiles, order, noise, grid, bad,
-         (double)cyc / (reps * ntiles * 4 * (order >= 3 ? 9 : 1)), cyc_noise);
+         (double)cyc / (reps * ntiles * 4 * ((order >= 3 && order != 10) ? 9 : 1)), cyc_noise);
   return bad ? 1 : 0;
 }
