@@ -350,6 +350,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       constexpr bool TILE_OUTER = decltype(outer_c)::value;
       constexpr int NTAPS = decltype(taps_c)::value;
       int a_stage_i = 0, a_par = 0, ws = 0, w_par = 0;
+      // (laundered through an opaque asm so that ptxas keeps the addresses in registers instead of re-deriving
+      //  them from SR_CgaCtaId at every wait / commit)
+      auto keep = [](uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
+      const uint32_t wfull0 = keep(smem_u32(&bar_w_full[0])), wempty0 = keep(smem_u32(&bar_w_empty[0]));
+      const uint32_t afull0 = keep(smem_u32(&bar_a_full[0])), aempty0 = keep(smem_u32(&bar_a_empty[0]));
       const uint32_t uN = static_cast<uint32_t>(N), uWp = static_cast<uint32_t>(Wp);
       for (int li = 0; li < my_groups; ++li) {
         const int buf = li % acc_bufs, useb = li / acc_bufs;
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const uint32_t acc = tmem + buf * acc_stride;
         for (int chunk = 0; chunk < nchunks; ++chunk) {
           const int stage = a_stage_i;
-          mbar_wait(&bar_a_full[stage], a_par);
+          mbar_wait_addr(afull0 + 8 * stage, a_par);
           tc_fence_after_sync();
           if (chunk == 0 && leader) RD_TRACE(0, li, 2);
           const uint32_t a_lo_stage = a_lo0 + stage * a_stage_u;
@@ -376,17 +381,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll
             for (int t = 0; t < NTAPS; ++t) {
               const uint32_t shift = NTAPS == 9 ? (t / 3) * uWp + (t % 3) : 0u;
-              if (!no_stream) { mbar_wait(&bar_w_full[ws], w_par); tc_fence_after_sync(); }
+              if (!no_stream) { mbar_wait_addr(wfull0 + 8 * ws, w_par); tc_fence_after_sync(); }
               if (leader) {
                 if (!skip_mma)
                   issue_tap<NT, TILE_OUTER>(acc, uN, a_lo_stage + shift, w_lo0 + ws * w_slab_u, kstep_a, kstep_w, desc_hi, idesc,
                                             (chunk | t) != 0);
-                if (!no_stream) umma_commit(&bar_w_empty[ws]);
+                if (!no_stream) umma_commit_addr(wempty0 + 8 * ws);
               }
               if (++ws == w_stages) { ws = 0; w_par ^= 1; }
             }
           }
-          if (leader) umma_commit(&bar_a_empty[stage]);  // operand stage reusable once these MMAs have read it
+          if (leader) umma_commit_addr(aempty0 + 8 * stage);  // operand stage reusable once these MMAs have read it
           if (++a_stage_i == a_stages) { a_stage_i = 0; a_par ^= 1; }
         }
         if (leader) {
@@ -743,13 +748,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               float sum[8], sq[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; sq[j] = 0.0f; }
-              for (int px = slice; px < P; px += 4 * PS) {
-                uint4 raw[4];
+              constexpr int SB = 4;  // (12 in flight was measured slower: the streaming variants spill at the 128-register cap)
+              for (int px = slice; px < P; px += SB * PS) {
+                uint4 raw[SB];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < SB; ++u)
                   if (px + u * PS < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + toff[px + u * PS]));
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < SB; ++u)
                   if (px + u * PS < P) {
                     float f[8];
                     unpack8(raw[u], f);
@@ -772,15 +778,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           const int which = (chunk * 64 < p.C[0]) ? 0 : 1;  // C[0] is a multiple of 64 whenever there are two sources
           const __nv_bfloat16* base = (which ? gb1 - p.C[0] : gb0) + chunk * 64;
           const int* toff = t_off + (which ? p.S * P : 0);
-          for (int b0 = xt; b0 < items; b0 += 8 * XFORM_THREADS) {
-            uint4 raw[8];
+          constexpr int NB = 8;
+          for (int b0 = xt; b0 < items; b0 += NB * XFORM_THREADS) {
+            uint4 raw[NB];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < NB; ++u) {
               const int item = b0 + u * XFORM_THREADS;
               if (item < items) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + toff[item >> 3] + (item & 7) * 8));
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < NB; ++u) {
               const int item = b0 + u * XFORM_THREADS;
               if (item < items) {
                 const int sp = item >> 3, kcl = item & 7;
@@ -903,6 +910,7 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   ConvParams best = p;
   static int wmax = -1, astream = 3;
   static double single_pen = 0.75, tie_eps = 0.0;
+  static int res2 = 0;
   if (wmax < 0) {
     const char* e = getenv("RD_CONV_WSTAGES");
     wmax = e ? atoi(e) : 4;
@@ -910,10 +918,23 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     if (wmax > MAX_W_STAGES) wmax = MAX_W_STAGES;
     if ((e = getenv("RD_CONV_ASTAGES_STREAM"))) astream = atoi(e) <= 2 ? 2 : 3;
     if ((e = getenv("RD_CONV_SINGLE_PEN"))) single_pen = atof(e);
+    if ((e = getenv("RD_CONV_RES2"))) res2 = atoi(e);
     if ((e = getenv("RD_CONV_TIE_EPS"))) tie_eps = atof(e);  // streamed filters: a larger group wins when within tie_eps
+  }
+  // RD_CONV_FORCE_NT="cin,n,h,nt;..." pins the tile count of the layers with that (C_in, C_out, H_in) -- geometry experiments
+  int force_nt = 0;
+  {
+    static const char* spec = getenv("RD_CONV_FORCE_NT");
+    for (const char* q = spec; q && *q;) {
+      int a = 0, b = 0, c = 0, d = 0;
+      if (sscanf(q, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a == cin && b == p.N && c == op.H_in) force_nt = d;
+      q = strchr(q, ';');
+      if (q) ++q;
+    }
   }
   for (int nt = 1; nt <= 4; ++nt) {
     if (nt * p.N > 512 || nt * 128 < p.rps) continue;
+    if (force_nt && nt != force_nt) continue;
     ConvParams c = p;
     c.n_tiles = nt;
     c.R = (nt * 128 + max_shift) | 1;
@@ -923,6 +944,10 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     c.a_stage_bytes = (8 * c.R * 16 + 127) / 128 * 128;
     c.a_stages = (p.nchunks == 1) ? 2 : 3;
     c.w_resident = 1;
+    if (res2 && conv_smem_layout(c).total > smem_cap && c.a_stages == 3) {
+      c.a_stages = 2;  // a resident filter is worth more than the third operand stage
+      if (conv_smem_layout(c).total > smem_cap) c.a_stages = 3;
+    }
     if (conv_smem_layout(c).total > smem_cap) {
       // Streamed filter: the ring has to cover the L2 latency of a slab at the rate the tensor core consumes them
       // (8-16 KB per ~600 cycles), i.e. tens of KB in flight -- it gets whatever shared memory two operand stages

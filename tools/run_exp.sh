@@ -2,5 +2,3 @@
 mkdir -p gpurun_out
 run() { name=$1; shift; env "$@" timeout 200 python tools/gpu_optime.py > gpurun_out/optime_$name.log 2>&1; echo "== $name: $(sed -n 1,3p gpurun_out/optime_$name.log | tr '\n' ' ')"; }
 run base RD_X=0
-run w8 RD_CONV_WSTAGES=8 RD_CONV_ASTAGES_STREAM=2
-run w6a3 RD_CONV_WSTAGES=6
