@@ -57,7 +57,8 @@ int rd_score_hk_f32(const float* x, const float* x_orig, const float* sigma, flo
                     size_t B, size_t D, int efs, int refls, float min_cutoff, void* stream);
 
 /* ---------------------------------------------------------------- noise */
-/* out[0..n) = the N(0,1) stream the fused step kernels draw for (seed, draw). n multiple of 4. */
+/* out[0..n) = the N(0,1) stream the fused step kernels draw for (seed, draw): element i is lane i%4 of Philox quad i/4
+ * (any n; quads are indexed over the flat tensor). */
 int rd_philox_normal_f32(float* out, size_t n, uint64_t seed, uint32_t draw, void* stream);
 
 /* ---------------------------------------------------------------- predictor / corrector */
