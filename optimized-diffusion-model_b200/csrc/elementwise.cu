@@ -440,11 +440,9 @@ __device__ __forceinline__ void pc_update_loop(const float* __restrict__ x, cons
                                                size_t D, uint64_t seed, uint32_t draw, bool vec_ok) {
   const size_t nq = (n + 3) >> 2;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nq; i += stride) {
+  auto load = [&](size_t i, float (&xs)[4], float (&vs)[4], float (&z)[4]) {
     const size_t i0 = 4 * i;
-    const bool whole = vec_ok && i0 + 4 <= n;
-    float xs[4], vs[4], z[4];
-    if (whole) {
+    if (vec_ok && i0 + 4 <= n) {
       const float4 xv = *reinterpret_cast<const float4*>(x + i0), vv = *reinterpret_cast<const float4*>(v + i0);
       xs[0] = xv.x; xs[1] = xv.y; xs[2] = xv.z; xs[3] = xv.w;
       vs[0] = vv.x; vs[1] = vv.y; vs[2] = vv.z; vs[3] = vv.w;
@@ -461,6 +459,9 @@ __device__ __forceinline__ void pc_update_loop(const float* __restrict__ x, cons
         z[u] = (in && zt) ? zt[i0 + u] : 0.0f;
       }
     }
+  };
+  auto finish = [&](size_t i, const float (&xs)[4], const float (&vs)[4], float (&z)[4]) {
+    const size_t i0 = 4 * i;
     if (!zt) philox_normal4(seed, draw, i, z);
     float xm[4], xn[4];
 #pragma unroll
@@ -476,7 +477,7 @@ __device__ __forceinline__ void pc_update_loop(const float* __restrict__ x, cons
       xn[u] = reflect1(__fadd_rn(m, __fmul_rn(bu, z[u])));
       if (MEAN) xm[u] = reflect1(m);
     }
-    if (whole) {
+    if (vec_ok && i0 + 4 <= n) {
       *reinterpret_cast<float4*>(x_out + i0) = make_float4(xn[0], xn[1], xn[2], xn[3]);
       if (MEAN) *reinterpret_cast<float4*>(x_mean_out + i0) = make_float4(xm[0], xm[1], xm[2], xm[3]);
     } else {
@@ -487,6 +488,15 @@ __device__ __forceinline__ void pc_update_loop(const float* __restrict__ x, cons
           if (MEAN) x_mean_out[i0 + u] = xm[u];
         }
     }
+  };
+  // two quads per iteration: both threads' loads are in flight before either quad's Philox / reflect arithmetic starts
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nq; i += 2 * stride) {
+    const size_t j = i + stride;
+    float xa[4], va[4], za[4], xb[4], vb[4], zb[4];
+    load(i, xa, va, za);
+    if (j < nq) load(j, xb, vb, zb);
+    finish(i, xa, va, za);
+    if (j < nq) finish(j, xb, vb, zb);
   }
 }
 
@@ -537,6 +547,21 @@ __global__ void __launch_bounds__(256) pc_predictor_kernel(const float* __restri
 }
 
 __global__ void step_advance_kernel(int32_t* ctr) { *ctr += 1; }
+
+// Grid of a grid-stride streaming kernel: exactly one resident wave (SMs x blocks that fit per SM), so that there is
+// no partial second wave (1184 blocks on 148 x 6 resident ones ran 1.33 waves).
+template <typename K>
+static inline int resident_grid(K kernel, size_t work_items, int threads) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 4;
+  }
+  size_t blocks = (work_items + threads - 1) / threads;
+  const size_t cap = static_cast<size_t>(kNumSMs) * per_sm;
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks < 1 ? 1 : blocks);
+}
 
 static inline int stream_grid(size_t work_items, int threads, int max_waves = 8) {
   size_t blocks = (work_items + threads - 1) / threads;
@@ -662,8 +687,9 @@ int rd_pc_corrector_apply(const float* x, const float* grad, const float* noise,
   RD_REQUIRE(x && grad && partial && x_out && B > 0 && D > 0 && nblk > 0, "rd_pc_corrector_apply: bad arguments");
   const size_t n = B * D;
   const int vec_ok = all_aligned16(x, grad, x_out, x_mean_out) && all_aligned16(noise, nullptr, nullptr, nullptr);
-  int grid = stream_grid((n + 3) / 4, 256, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t half = ((n + 3) / 4 + 1) / 2;  // two quads per thread and iteration
+  int grid = x_mean_out ? resident_grid(pc_corrector_apply_kernel<true>, half, 256) : resident_grid(pc_corrector_apply_kernel<false>, half, 256);
   if (x_mean_out)
     pc_corrector_apply_kernel<true><<<grid, 256, 0, st>>>(x, grad, noise, partial, nblk, snr, x_out, x_mean_out, stats_out,
                                                           B, n, seed, draw_base, step_ctr, noise_step_stride, vec_ok);
@@ -682,9 +708,9 @@ int rd_pc_predictor_step(const float* x, const float* score, const float* z, con
   RD_REQUIRE(!advance_ctr || step_ctr, "rd_pc_predictor_step: advance_ctr needs step_ctr");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int vec_ok = all_aligned16(x, score, x_out, x_mean_out) && all_aligned16(z, nullptr, nullptr, nullptr);
-  int grid = stream_grid((n + 3) / 4, 256, 8);
+  const size_t half = ((n + 3) / 4 + 1) / 2;
 #define RD_PRED(M, P)                                                                                              \
-  pc_predictor_kernel<M, P><<<grid, 256, 0, st>>>(x, score, z, g_table, dt, sqrt_dt, x_out, x_mean_out, n, seed, \
+  pc_predictor_kernel<M, P><<<resident_grid(pc_predictor_kernel<M, P>, half, 256), 256, 0, st>>>(x, score, z, g_table, dt, sqrt_dt, x_out, x_mean_out, n, seed, \
                                                   draw_base, step_ctr, noise_step_stride, D, vec_ok)
   if (x_mean_out) { if (g_per_sample) RD_PRED(true, true); else RD_PRED(true, false); }
   else            { if (g_per_sample) RD_PRED(false, true); else RD_PRED(false, false); }
