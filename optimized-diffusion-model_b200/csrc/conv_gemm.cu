@@ -922,8 +922,15 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     if ((e = getenv("RD_CONV_TIE_EPS"))) tie_eps = atof(e);  // streamed filters: a larger group wins when within tie_eps
   }
   // RD_CONV_FORCE_NT="cin,n,h,nt;..." pins the tile count of the layers with that (C_in, C_out, H_in) -- geometry experiments
-  int force_nt = 0;
+  int force_nt = 0, force_s = 0;
   {
+    static const char* sspec = getenv("RD_CONV_FORCE_S");  // "cin,n,h,S;...": cap on the samples per group
+    for (const char* q = sspec; q && *q;) {
+      int a = 0, b = 0, c = 0, d = 0;
+      if (sscanf(q, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a == cin && b == p.N && c == op.H_in) force_s = d;
+      q = strchr(q, ';');
+      if (q) ++q;
+    }
     static const char* spec = getenv("RD_CONV_FORCE_NT");
     for (const char* q = spec; q && *q;) {
       int a = 0, b = 0, c = 0, d = 0;
@@ -940,6 +947,7 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     c.R = (nt * 128 + max_shift) | 1;
     c.S = (nt * 128) / p.rps;
     if (op.samples_per_cta > 0 && op.samples_per_cta < c.S) c.S = op.samples_per_cta;
+    if (force_s > 0 && force_s < c.S) c.S = force_s;
     c.acc_bufs = (2 * nt * p.N <= 512) ? 2 : 1;
     c.a_stage_bytes = (8 * c.R * 16 + 127) / 128 * 128;
     c.a_stages = (p.nchunks == 1) ? 2 : 3;
