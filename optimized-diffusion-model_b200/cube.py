@@ -32,6 +32,9 @@ def sample_hk(x, sigma):
 
 
 def score_hk(x, x_orig, sigma, efs=20, refls=10, min_cutoff=1e-2):
-    """Score of the reflected heat kernel (cube.py:149-193): eigenfunction series for
-    sigma^2/2 > min_cutoff, method of images below; one fused kernel, no temporaries."""
+    """Score of the reflected heat kernel (cube.py:149-193).  The reference evaluates sigma^2/2 > min_cutoff with
+    `efs` cosine modes and the rest with images |m| <= `refls`; both series are the same function, and the fused
+    kernel sums whichever converged form is cheaper per sample -- truncated series
+    (efs / refls below what convergence needs) and the reference's 1e-12 denominator epsilon are reproduced as
+    written.  One launch, no temporaries."""
     return _ops.score_hk(x, x_orig, sigma, efs=efs, refls=refls, min_cutoff=min_cutoff)
