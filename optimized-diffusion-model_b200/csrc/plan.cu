@@ -57,8 +57,12 @@ static int enqueue_iteration(rd_sampler* s, cudaStream_t st, int* launches) {
       return rc;
     count += 2;
   }
-  if ((rc = rd_plan_run(d.forward, st)) != RD_OK) return rc;
-  count += rd_plan_size(d.forward);
+  // The time-embedding projections depend on (step, labels) only, not on x: when a corrector forward of this
+  // iteration has already filled them, the predictor forward skips the temb launch (the step counter advances after
+  // the predictor).
+  const int skip = (d.n_corrector_steps > 0 && rd_plan_size(d.forward) > 1 && d.forward->ops[0].kind == RD_OP_TEMB) ? 1 : 0;
+  if ((rc = rd_plan_run_range(d.forward, skip, rd_plan_size(d.forward) - skip, st)) != RD_OK) return rc;
+  count += rd_plan_size(d.forward) - skip;
   const float* z = d.noise_tape ? d.noise_tape + (draws_per_step - 1) * n : nullptr;
   if ((rc = rd_pc_predictor_step(d.x, d.score, z, d.g_table, d.dt, d.sqrt_dt, d.x, nullptr, d.B, d.D, d.seed, 0, d.step_ctr,
                                  draws_per_step * n, 1, 0, st)) != RD_OK)
@@ -111,6 +115,7 @@ int rd_sampler_create(const rd_sampler_desc* d, rd_sampler** out) {
   RD_REQUIRE(s, "rd_sampler_create: out of memory");
   s->d = *d;
   s->launches_per_iter = (d->n_corrector_steps + 1) * rd_plan_size(d->forward) + 2 * d->n_corrector_steps + 2;
+  if (d->n_corrector_steps > 0 && rd_plan_size(d->forward) > 1 && d->forward->ops[0].kind == RD_OP_TEMB) s->launches_per_iter -= 1;
   *out = s;
   return RD_OK;
 }
