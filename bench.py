@@ -34,6 +34,18 @@ for p in (ROOT, PKG):
 
 import torch  # noqa: E402
 
+_JSON_OUT = sys.stdout
+
+
+def _isolate_stdout():
+    """stdout carries exactly ONE JSON line per run: keep a private duplicate of the descriptor for that line and point
+    fd 1 at stderr for everything else (NCCL prints its "NCCL version ..." banner on stdout)."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
 SDE_N = 1000
 ITERS_PER_PASS = SDE_N - 1          # sampling.py:330 skips the last grid point
 FLOP_PER_SAMPLE_FORWARD = 207.374848e6   # 8x9, attention at 8 (BASELINE.md section 2, torch FlopCounter, 2*MAC)
@@ -152,7 +164,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def _latest_traffic_profile():
@@ -191,6 +203,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2", action="store_true", help="skip the reflect / score_hk / fused-update HBM microbench")
     args = ap.parse_args()
+    _isolate_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,9 +220,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION prints
-        # "NCCL version ..." on stdout) goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__ as entry
@@ -379,7 +389,7 @@ def main():
             "clocks": clk, "roofline": roof, "hbm_kernels": {"shape": "[2^20,1,8,9] fp32 (C2)", "peak_GBps": pk["hbm_gbs"],
                                                               "peak_source": pk["source"], "rows": hbm},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_iter * K}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
