@@ -1,7 +1,7 @@
 """BASELINE config C2: cube.reflect / cube.score_hk / fused PC-update microbench on synthetic [2^20,1,8,9] latents
 across the VESDE sigma range on one B200, through the C ABI with pre-allocated buffers.
 
-Every kernel is timed with CUDA events on torch's current stream (the stream the C ABI launches on), 3 warm-up
+Every kernel is timed with CUDA events on torch's current stream (the stream the C ABI launches on), 10 warm-up
 launches then `--reps` timed ones; inputs are 302 MB each (> 126 MB L2), so there is no cross-iteration reuse.
 GB/s = ALGORITHMIC bytes (reflect 8 B/element; score_hk 12 B/element + 4 B/sample; fused
 predictor / corrector apply 12 B/element with in-kernel Philox noise; corrector norm pass 4 B/element) over the
@@ -32,7 +32,7 @@ def hbm_peak():
 
 
 def timed(fn, reps):
-    for _ in range(3):
+    for _ in range(10):   # first launches on freshly allocated buffers run slow (seen on `reflect`, the first case)
         fn()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
