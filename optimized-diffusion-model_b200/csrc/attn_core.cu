@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
   constexpr int TP = 16 * T16;
   constexpr int C = ATT_C;
   extern __shared__ __align__(16) unsigned char smraw[];
+  // the conv launch that follows may start its prologue as SMs free up (it waits for this grid before reading `out`)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __nv_bfloat16* Wq = reinterpret_cast<__nv_bfloat16*>(smraw);  // [3C][AB_LD]
   __nv_bfloat16* Wp = Wq + 3 * C * AB_LD;                       // [C][AB_LD]
   // Each team (T16 warps, one sample at a time) owns two buffers, each used twice: raw rows -> (dead after

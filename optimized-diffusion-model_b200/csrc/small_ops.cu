@@ -7,6 +7,7 @@
 //                   (ncsnpp.py:343-347, models/utils.py:124-138), fp32 score out
 #include "rd_common.h"
 #include <cuda_bf16.h>
+#include "rd_ptx.cuh"
 
 namespace rd {
 
@@ -149,6 +150,8 @@ __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ 
                                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B,
                                                       int B2, int Cin, int Cout, int H, int W) {
   extern __shared__ __align__(16) float sw[];  // [Cin*9][Cout] (tap-major) + bias[Cout]
+  // the conv launch that follows may start its prologue as SMs free up (it waits for this grid before reading `out`)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int wn = Cout * Cin * 9;
   for (int i = threadIdx.x; i < wn; i += blockDim.x) {
     const int co = i / (Cin * 9), t = i - co * (Cin * 9);
@@ -157,11 +160,14 @@ __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ 
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[wn + i] = bias[i];
   __syncthreads();
   const int P = H * W;
-  const int total = B2 * P;
+  // B2 is B or a multiple of it (x.repeat(2,1,1,1) under classifier-free guidance): every distinct pixel is computed
+  // once and stored B2/B times
+  const int total = B * P, copies = B2 / B;
+  const size_t copy_stride = static_cast<size_t>(B) * P * Cout;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
     const int b2 = pix / P, px = pix - b2 * P;
     const int yh = px / W, xw = px - yh * W;
-    const float* xb = x + static_cast<size_t>(b2 % B) * Cin * P;  // x.repeat(2,1,1,1)
+    const float* xb = x + static_cast<size_t>(b2) * Cin * P;
     for (int c0 = 0; c0 < Cout; c0 += 64) {
       float acc[64];
 #pragma unroll
@@ -188,14 +194,14 @@ __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ 
         }
       __nv_bfloat16* dst = out + static_cast<size_t>(pix) * Cout + c0;
 #pragma unroll
-      for (int j8 = 0; j8 < 8; ++j8) {
-        uint32_t pk[4];
+      for (int j16 = 0; j16 < 4; ++j16) {   // whole 32-byte sectors per store
+        u32x8 pk;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(acc[8 * j8 + 2 * j], acc[8 * j8 + 2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(acc[16 * j16 + 2 * j], acc[16 * j16 + 2 * j + 1]);
+          pk.v[j] = *reinterpret_cast<uint32_t*>(&h);
         }
-        *reinterpret_cast<uint4*>(dst + 8 * j8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int cp = 0; cp < copies; ++cp) st_global_256(dst + cp * copy_stride + 16 * j16, pk);
       }
     }
   }
@@ -206,8 +212,9 @@ int inconv_launch(const rd_op_inconv& op, cudaStream_t st) {
   RD_REQUIRE(op.C_out % 64 == 0, "in_conv: C_out must be a multiple of 64");
   const int smem = (op.C_out * op.C_in * 9 + op.C_out) * 4;
   RD_REQUIRE(smem <= 48 * 1024, "in_conv: weights do not fit shared memory");
-  const size_t total = static_cast<size_t>(op.B2) * op.H * op.W;
-  RD_REQUIRE(total < (1u << 31), "in_conv: batch too large");
+  RD_REQUIRE(op.B2 % op.B == 0, "in_conv: B2 must be a multiple of B");
+  const size_t total = static_cast<size_t>(op.B) * op.H * op.W;
+  RD_REQUIRE(static_cast<size_t>(op.B2) * op.H * op.W < (1u << 31), "in_conv: batch too large");
   size_t blocks = (total + 255) / 256;
   if (blocks > static_cast<size_t>(kNumSMs) * 16) blocks = static_cast<size_t>(kNumSMs) * 16;
   in_conv_kernel<<<static_cast<unsigned>(blocks), 256, smem, st>>>(op.x, op.w, op.bias, static_cast<__nv_bfloat16*>(op.out),
