@@ -355,6 +355,8 @@ def main():
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_c2
+            torch.cuda.empty_cache()   # fresh, contiguous allocations for the four 302 MB buffers (blocks recycled from the
+            #                            sampler passes above cost `reflect` a quarter of its bandwidth)
             warm = torch.rand((1 << 24,), device=dev)
             for _ in range(50):   # the CPU-side bookkeeping above leaves the GPU idle; bring clocks back up first
                 warm.mul_(1.0001)
