@@ -174,3 +174,23 @@ def test_engine_plan_accounting():
     # against Engine.conv_flops_per_sample in tests/test_gpu_network.py
     assert abs(total / 1e6 - 187.63) < 0.01, total / 1e6
     assert spec.levels == 3 and spec.nf == 64
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """The driver parses bench.py's stdout: exactly one JSON line, whatever the libraries underneath print (the NCCL
+    banner goes to stdout by default).  Run the CPU reference arm on a tiny sample and check the contract keys."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ref-batch", "8"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
