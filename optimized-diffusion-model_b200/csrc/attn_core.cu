@@ -162,6 +162,12 @@ int attn_launch(const rd_op_attn& op, cudaStream_t st) {
 // memory once.  Projection weights sit in shared memory for the CTA's lifetime.
 namespace rd {
 
+__device__ __forceinline__ float ab_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int AB_LD = 72;  // bf16 row stride (144 B): conflict-free 32-bit fragment loads and ldmatrix rows
 
 constexpr int AB_G = 2;  // samples in flight per CTA: independent teams of T16 warps that share the weights in smem
@@ -337,13 +343,16 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
       project8(xa, Wq, 8 + nb, ck);
       project8(xa, Wq, 16 + nb, cv);
       const int c = nb * 8 + 2 * q4;
+      // No bias on k and v here: a key bias adds the same q.b_k to every score of a query row, which softmax cancels
+      // exactly, and since the probabilities sum to one the value bias passes through P V unchanged -- the host folds
+      // it into the projection bias (b_proj + b_v W_proj, rdb200/pack.py `proj.bias_fused`).
       if (r0 < T) {
-        *reinterpret_cast<uint32_t*>(Ks + r0 * AB_LD + c) = pack_bf16(ck[0] + s_bq[C + c], ck[1] + s_bq[C + c + 1]);
-        *reinterpret_cast<uint32_t*>(Vs + r0 * AB_LD + c) = pack_bf16(cv[0] + s_bq[2 * C + c], cv[1] + s_bq[2 * C + c + 1]);
+        *reinterpret_cast<uint32_t*>(Ks + r0 * AB_LD + c) = pack_bf16(ck[0], ck[1]);
+        *reinterpret_cast<uint32_t*>(Vs + r0 * AB_LD + c) = pack_bf16(cv[0], cv[1]);
       }
       if (r1 < T) {
-        *reinterpret_cast<uint32_t*>(Ks + r1 * AB_LD + c) = pack_bf16(ck[2] + s_bq[C + c], ck[3] + s_bq[C + c + 1]);
-        *reinterpret_cast<uint32_t*>(Vs + r1 * AB_LD + c) = pack_bf16(cv[2] + s_bq[2 * C + c], cv[3] + s_bq[2 * C + c + 1]);
+        *reinterpret_cast<uint32_t*>(Ks + r1 * AB_LD + c) = pack_bf16(ck[2], ck[3]);
+        *reinterpret_cast<uint32_t*>(Vs + r1 * AB_LD + c) = pack_bf16(cv[2], cv[3]);
       }
     }
     team_sync();
@@ -354,27 +363,33 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
     for (int nb = 0; nb < 2 * T16; ++nb) {
       project8(qa, Ks, nb, s[nb]);  // keys are rows of Ks with the 64 channels contiguous: same operand form as a weight
     }
+    // softmax_j(scale * s_ij): the row maximum is taken on the raw scores (scale > 0), keys >= T are masked only in the
+    // 8-key blocks that reach past T, and exp(scale (s - m)) is one FMA + ex2 with c = scale * log2(e)
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int nb = 0; nb < 2 * T16; ++nb) {
+      if (nb * 8 + 8 > T) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool ok = (nb * 8 + 2 * q4 + e) < T;
-        s[nb][e] = ok ? s[nb][e] * scale : -INFINITY;
-        s[nb][2 + e] = ok ? s[nb][2 + e] * scale : -INFINITY;
-        m0 = fmaxf(m0, s[nb][e]);
-        m1 = fmaxf(m1, s[nb][2 + e]);
+        for (int e = 0; e < 2; ++e) {
+          const bool ok = (nb * 8 + 2 * q4 + e) < T;
+          s[nb][e] = ok ? s[nb][e] : -INFINITY;
+          s[nb][2 + e] = ok ? s[nb][2 + e] : -INFINITY;
+        }
       }
+      m0 = fmaxf(m0, fmaxf(s[nb][0], s[nb][1]));
+      m1 = fmaxf(m1, fmaxf(s[nb][2], s[nb][3]));
     }
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    const float cexp = scale * 1.4426950408889634f;
+    const float mc0 = -m0 * cexp, mc1 = -m1 * cexp;
     float l0 = 0.0f, l1 = 0.0f;
 #pragma unroll
     for (int nb = 0; nb < 2 * T16; ++nb) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        s[nb][e] = __expf(s[nb][e] - m0);
-        s[nb][2 + e] = __expf(s[nb][2 + e] - m1);
+        s[nb][e] = ab_ex2(fmaf(s[nb][e], cexp, mc0));        // ex2(-inf) = 0 for masked keys
+        s[nb][2 + e] = ab_ex2(fmaf(s[nb][2 + e], cexp, mc1));
         l0 += s[nb][e];
         l1 += s[nb][2 + e];
       }

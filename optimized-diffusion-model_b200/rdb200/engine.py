@@ -198,7 +198,7 @@ class Engine:
             a = op.u.attn_block
             a.x, a.out = x.ptr, out.ptr
             a.wqkv_t, a.wproj_t = self.w.ptr(p + ".wqkv_t"), self.w.ptr(p + ".wproj_t")
-            a.bqkv, a.bproj = self.w.ptr(p + ".qkv.bias"), self.w.ptr(p + ".proj.bias")
+            a.bqkv, a.bproj = self.w.ptr(p + ".qkv.bias"), self.w.ptr(p + ".proj.bias_fused")
             a.gamma, a.beta = self.w.ptr(p + ".GroupNorm_0.weight"), self.w.ptr(p + ".GroupNorm_0.bias")
             a.B2, a.T, a.C, a.groups, a.eps, a.out_scale = self.B2, x.H * x.W, Cc, min(Cc // 4, 32), 1e-6, rs
             self._add(op, p)

@@ -111,6 +111,8 @@ class PackedWeights:
             # fused attention kernel: weights transposed to [out][in] bf16 rows padded to 72 (conflict-free fragments)
             self._put(f"{p}.wqkv_t", pad_rows(qkv.t().contiguous(), 72))
             self._put(f"{p}.wproj_t", pad_rows(f32(sd[f"{p}.NIN_3.W"]).t().contiguous(), 72))
+            # fused kernel: k / v carry no bias (csrc/attn_core.cu); the value bias reaches the output as b_v @ W_3
+            self._put(f"{p}.proj.bias_fused", f32(sd[f"{p}.NIN_3.b"]) + f32(sd[f"{p}.NIN_2.b"]) @ f32(sd[f"{p}.NIN_3.W"]))
         for k in list(sd.keys()):
             if (k.startswith("downsample.") or k.startswith("upsample.")) and k.endswith(".Conv_0.weight"):
                 p = k[: -len(".weight")]
