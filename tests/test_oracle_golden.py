@@ -103,3 +103,45 @@ def test_sampler_tape_replay(tag, corrector):
     assert bool(O.inside(x).all())
     assert float((x - torch.from_numpy(g["x_final"])).abs().max()) <= 5e-4
     assert int(g["nfe"]) == N * 2  # the reference reports N*(n_steps+1) regardless of the corrector
+
+
+def test_identities_the_kernels_rely_on_fp64():
+    """Two exact reformulations used by the CUDA kernels, checked in fp64 on the oracle (no GPU involved):
+    (1) csrc/attn_core.cu drops the key bias (softmax-invariant) and folds the value bias into the output projection
+        bias (rdb200/pack.py `proj.bias_fused`);
+    (2) csrc/elementwise.cu evaluates score_hk above the reference's branch cutoff with the image sum instead of the
+        eigen-series (same function by Poisson summation; the 1e-12 denominator epsilon is rescaled by sqrt(4 pi t))."""
+    import numpy as np
+    from oracle import rd_oracle as O
+    g = torch.Generator().manual_seed(12)
+    # ---- (1) attention block with and without k / v biases
+    B, C, H, W = 3, 64, 8, 9
+    sd = {}
+    for j in range(4):
+        sd[f"a.NIN_{j}.W"] = torch.randn(C, C, generator=g, dtype=torch.float64) * 0.2
+        sd[f"a.NIN_{j}.b"] = torch.randn(C, generator=g, dtype=torch.float64)
+    sd["a.GroupNorm_0.weight"] = torch.rand(C, generator=g, dtype=torch.float64) + 0.5
+    sd["a.GroupNorm_0.bias"] = torch.randn(C, generator=g, dtype=torch.float64)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    ref = O.attnblock(x, sd, "a")
+    sd2 = dict(sd)
+    sd2["a.NIN_1.b"] = torch.zeros(C, dtype=torch.float64)
+    sd2["a.NIN_2.b"] = torch.zeros(C, dtype=torch.float64)
+    sd2["a.NIN_3.b"] = sd["a.NIN_3.b"] + sd["a.NIN_2.b"] @ sd["a.NIN_3.W"]
+    assert float((O.attnblock(x, sd2, "a") - ref).abs().max()) < 1e-12
+    # ---- (2) eigen-series vs image sum of the reflected heat-kernel score, t = sigma^2/2 in (0.01, 0.214]
+    n = 4096
+    for sigma in (0.1415, 0.2, 0.3, 0.5, 0.65):
+        t = sigma ** 2 / 2
+        x0 = torch.rand(n, 1, generator=g, dtype=torch.float64)
+        xx = O.reflect(x0 + sigma * torch.randn(n, 1, generator=g, dtype=torch.float64))
+        sg = torch.full((n,), sigma, dtype=torch.float64)
+        ef = O._score_hk_ef(xx, x0, sg ** 2 / 2, 40)
+        im = O._score_hk_refl(xx, x0, sg ** 2 / 2, 10)
+        scale = float(ef.abs().max())
+        assert float((ef - im).abs().max()) <= 1e-9 * scale + 1e-9, sigma
+        # the kernel's truncations at this t: Kc modes / Mc image pairs change nothing an fp32 result could see
+        Kc = int(np.ceil(np.sqrt(17.5 / (np.pi ** 2 * t)))) + 1
+        Mc = int(np.ceil(np.sqrt((70 * t + 1) / 4)))
+        assert float((O._score_hk_ef(xx, x0, sg ** 2 / 2, Kc) - ef).abs().max()) <= 3e-7 * scale
+        assert float((O._score_hk_refl(xx, x0, sg ** 2 / 2, Mc) - im).abs().max()) <= 3e-7 * scale
