@@ -1,7 +1,7 @@
 """Diagnostic run on the GPU box: element-wise kernels and the network forward against the
 committed golden fixtures / the oracle.  Prints error magnitudes; asserts nothing."""
 import os, sys, time, types
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "optimized-diffusion-model_b200"))
 import numpy as np, torch
 from oracle import rd_oracle as O

@@ -1,6 +1,6 @@
 """Second diagnostic: sampler parity (free-running, teacher-forced) and a first timing."""
 import os, sys, time, types
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "optimized-diffusion-model_b200"))
 import numpy as np, torch
 from oracle import rd_oracle as O

@@ -1,7 +1,7 @@
 """Diagnostic: guided-score error of the CUDA path vs fp32 oracle across noise levels, next to the
 PyTorch bf16-autocast floor (same weights / inputs).  Run on the GPU box."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "optimized-diffusion-model_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from oracle import rd_oracle as O
