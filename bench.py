@@ -111,13 +111,83 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_iteration_time(B, steps, warmup, threads):
-    """The reference's algorithm on the host cores: the oracle port (oracle/rd_oracle.py, bit-identical to
-    the reference on the golden fixtures) -- one PC iteration = 2 guided scores at 2B + both updates."""
+def static_config(B, world):
+    """The workload description shared verbatim by both arms' JSON lines (run-dependent facts live outside `config`)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+            "step": "one PC iteration (2 CFG score evaluations + fused corrector and predictor updates); "
+                    "value = global_batch / (999*ms_per_step + all-gather)",
+            "l2": "activations of one iteration (>5 GB at 2B=16384) exceed the 126 MB L2; no flush needed",
+            "parallelism": f"batch-sharded x{world}, no collective in the loop"}
+
+
+def _ref_available():
+    from oracle import fetch_ref
+    return fetch_ref.available() and fetch_ref.verify()
+
+
+def stock_reference_pass(ref, B, N, device, threads=None, weights_seed=0):
+    """ONE call of the unmodified reference's public API -- sampling.get_sampling_fn(config, sde, shape, eps, device)
+    (model, weight=1.5, class_labels=...) -- with a forward-pre-hook on the model that only records timestamps
+    (two network calls per PC iteration).  Returns (seconds for the whole call, timestamps, samples)."""
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = model_config()
+    torch.manual_seed(weights_seed)
+    model = ref.mutils.create_model(cfg).to(device).eval()   # untouched reference init, like our arm
+    sde = ref.sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=N)
+    fn = ref.sampling.get_sampling_fn(cfg, sde, (B, 1, 8, 9), 1e-5, device)
+    labels = torch.rand((B, 1), generator=torch.Generator().manual_seed(1)).to(device)
+    stamps = []
+    cuda = torch.device(device).type == "cuda"
+
+    def hook(_m, _a):
+        if cuda:
+            torch.cuda.synchronize()
+        stamps.append(time.perf_counter())
+    h = model.register_forward_pre_hook(hook)
+    if cuda:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, _ = fn(model, weight=1.5, class_labels=labels)
+    if cuda:
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    h.remove()
+    return t1 - t0, stamps + [t1], x
+
+
+def cpu_reference_c1(steps, warmup, passes=3):
+    """BASELINE config C1 in full (batch 128, 100 steps, all host threads), `passes` times; the best pass is reported.
+    ms_per_step = K consecutive PC iterations of that pass after W warm-up iterations (every iteration does the same
+    work).  Falls back to the oracle port when oracle/_ref did not travel (kind says which)."""
+    threads = os.cpu_count() or 1
+    B, N = 128, 100
+    if _ref_available():
+        from oracle import fetch_ref
+        if steps + warmup > N - 1:
+            N = steps + warmup + 1
+        best = None
+        with fetch_ref.imported() as ref:
+            import contextlib, io
+            for _ in range(passes):
+                with contextlib.redirect_stdout(io.StringIO()):   # the stock constructor prints three [DEBUG] lines
+                    total, st, x = stock_reference_pass(ref, B, N, "cpu", threads)
+                ms = 1e3 * (st[2 * (warmup + steps)] - st[2 * warmup]) / steps
+                if best is None or ms < best[0]:
+                    best = (ms, total)
+                assert bool(((x >= 0) & (x <= 1)).all())
+        ms, total = best
+        sample = (f"UNMODIFIED reference (oracle/_ref copy of Reflected-Diffusion, sha-verified), stock "
+                  f"sampling.get_sampling_fn on the CPU, fp32, {threads} threads: BASELINE config C1 in full (batch {B}, "
+                  f"{N} steps, CFG w=1.5) best of {passes} passes = {total:.2f} s per pass; ms_per_step = {steps} consecutive PC "
+                  f"iterations after {warmup} warm-up iterations of that pass; value extrapolates the per-iteration time to "
+                  f"the 999 iterations of the 1000-step sampler; loadavg {os.getloadavg()[0]:.1f}")
+        return {"ms": ms, "B": B, "kind": "reference", "cores": threads, "sample": sample, "c1_pass_seconds": total}
+    # ---- fallback: the oracle port (bit-identical to the reference on the golden fixtures)
     from oracle import rd_oracle as O
     torch.set_num_threads(threads)
     cfg = O.NetConfig()
-    sd = O.synth_state_dict(cfg, seed=0, degenerate=True)  # magnitude pattern of the untouched reference init
+    sd = O.synth_state_dict(cfg, seed=0, degenerate=True)
     sched = O.VESchedule(0.01, 5.0, SDE_N, 1.0, 1e-5)
     scfg = O.SamplerConfig()
     g = torch.Generator().manual_seed(2)
@@ -135,60 +205,80 @@ def cpu_reference_iteration_time(B, steps, warmup, threads):
             x, _, _ = O.corrector_step(x, grad, noise[0], scfg.snr)
             score = O.guided_score(x, sig, labels, 1.5, sd, cfg)
             x, _ = O.predictor_step(x, score, sched.diffusion(vec_t), SDE_N, noise[1])
-            dt = time.perf_counter() - t0
             if i >= warmup:
-                times.append(dt)
-    return times
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    sample = (f"oracle/_ref absent: ORACLE PORT of the reference sampler (fp32 PyTorch CPU), batch {B}, {steps} PC iterations "
+              f"after {warmup} warm-up, extrapolated to 999 iterations; loadavg {os.getloadavg()[0]:.1f}")
+    return {"ms": ms, "B": B, "kind": "port", "cores": threads, "sample": sample, "c1_pass_seconds": None}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    B = args.ref_batch
-    # bounded sample: keep the whole K-step run within ~2 minutes by shrinking the per-step batch if needed
-    probe = cpu_reference_iteration_time(B, 1, 1, threads)[0]
-    budget_s = 120.0
-    if probe * (args.steps + args.warmup) > budget_s:
-        B = max(8, int(B * budget_s / (probe * (args.steps + args.warmup))) // 8 * 8)
-    times = cpu_reference_iteration_time(B, args.steps, args.warmup, threads)
-    ms = 1e3 * sum(times) / len(times)
-    value = B / (ITERS_PER_PASS * ms / 1e3)
-    sample = (f"oracle port of the reference sampler (fp32 PyTorch CPU, TF32 n/a), batch {B}, {args.steps} PC iterations "
-              f"timed after {args.warmup} warm-up, extrapolated linearly to the 999 iterations of a full pass; "
-              f"loadavg {os.getloadavg()[0]:.1f}")
+    r = cpu_reference_c1(args.steps, args.warmup)
+    value = r["B"] / (ITERS_PER_PASS * r["ms"] / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "reference_batch": B,
-                                                           "step": "one PC iteration on the host CPU cores"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": static_config(args.batch, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                             "batch": r["B"], "c1_pass_seconds": r["c1_pass_seconds"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
-def _latest_traffic_profile():
-    """profiles/*_conv_traffic.json is written by tools/summarise_ncu.py from an `ncu --metrics dram__bytes_*` capture
-    of the conv launches of this same workload (tools/run_gpu_round.sh); the newest round's file is used."""
-    import glob
-    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "*_conv_traffic.json")))
-    if not files:
-        return None, None
+def eager_gpu_baseline(dev, B, iters=20):
+    """The stock reference sampler on the SAME GPU in eager fp32 (TF32 off): what a user of sampling.py gets on this card
+    today.  One warm-up call (cuDNN autotune, allocator) then one timed call of `iters` PC iterations (an RVESDE with
+    N = iters + 1 grid points runs exactly `iters` iterations; the work per iteration does not depend on the grid)."""
+    if not _ref_available():
+        return {"unavailable": "oracle/_ref did not travel"}
+    from oracle import fetch_ref
+    import contextlib, io
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        with open(files[-1]) as f:
-            return json.load(f), os.path.relpath(files[-1], os.path.dirname(os.path.abspath(__file__)))
-    except Exception:
-        return None, None
+        with fetch_ref.imported() as ref, contextlib.redirect_stdout(io.StringIO()):
+            stock_reference_pass(ref, B, 4, dev)
+            total, st, x = stock_reference_pass(ref, B, iters + 1, dev)
+        ms = 1e3 * (st[-1] - st[0]) / iters
+        inside = bool(((x >= 0) & (x <= 1)).all())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+    return {"value": B / (ITERS_PER_PASS * ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B, "iterations": iters,
+            "kind": "reference", "all_samples_inside_cube": inside,
+            "what": "unmodified reference sampling.get_sampling_fn on this GPU, eager PyTorch fp32 (cudnn/matmul TF32 off), "
+                    "same model / SDE / guidance as our arm; per-iteration time extrapolated to 999 iterations"}
 
 
-def conv_traffic_bytes():
-    js, _ = _latest_traffic_profile()
-    return None if js is None else js.get("dram_bytes_per_launch")
+def _conv_source_sha():
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("conv_gemm.cu", "rd_ptx.cuh"):
+        with open(os.path.join(PKG, "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
-def conv_traffic_source():
-    js, path = _latest_traffic_profile()
-    return None if js is None else "%s (ncu dram__bytes_read+write per conv launch, B=8192)" % path
+def conv_traffic():
+    """`roofline.traffic`: DRAM bytes per conv launch from an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
+    capture of this workload (tools/run_ncu_traffic.sh -> tools/summarise_ncu.py writes profiles/*_conv_traffic.json and
+    stamps it with the sha of the kernel sources it profiled).  A capture of OTHER sources is refused: traffic = null."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_conv_traffic.json")))
+    sha = _conv_source_sha()
+    for path in reversed(files):
+        try:
+            with open(path) as f:
+                js = json.load(f)
+        except Exception:
+            continue
+        if js.get("kernel_source_sha") == sha:
+            return js.get("dram_bytes_per_launch"), "%s (ncu dram__bytes_read+write per conv launch, B=8192, kernel sources %s)" % (
+                os.path.relpath(path, ROOT), sha)
+    return None, "no ncu capture of the current kernel sources (%s) under profiles/ -- stale captures are not reported" % sha
 
 
 def main():
@@ -198,7 +288,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8192, help="samples per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-batch", type=int, default=128)
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: total batch split evenly over the GPUs (BASELINE config C4 = 65536)")
+    ap.add_argument("--weight", type=float, default=1.5, help="classifier-free guidance weight (C3 sweep)")
+    ap.add_argument("--per-sample-weight", action="store_true", help="w_b = weight * U[0,1] per sample (run_train.py:173)")
+    ap.add_argument("--no-eager-gpu", action="store_true", help="skip the stock-reference-on-this-GPU baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2", action="store_true", help="skip the reflect / score_hk / fused-update HBM microbench")
@@ -234,6 +328,11 @@ def main():
     from rdb200 import dist as rdd
 
     B = args.batch
+    scaling = "weak"
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the number of GPUs")
+        B, scaling = args.global_batch // world, "strong"
     cfg = model_config()
     torch.manual_seed(0)
     model = mutils.create_model(cfg).to(dev).eval()   # untouched reference init: timing is weight-independent
@@ -244,8 +343,12 @@ def main():
     eng = model.rd_sampler_engine(B, 8, 9, dev, sde, 1e-5, 0.01, 1, cfg=True)
     seed = rdd.philox_seed_for_rank(3, rank)
 
+    weight = args.weight
+    if args.per_sample_weight:
+        weight = (args.weight * torch.rand((B,), generator=torch.Generator().manual_seed(5 + rank))).to(dev)
+
     def run_iters(n, start=0):
-        return eng.sample(x0, labels, 1.5, seed=seed, use_graph=True, n_iter=n, start_step=start)
+        return eng.sample(x0, labels, weight, seed=seed, use_graph=True, n_iter=n, start_step=start)
 
     # ---- warm-up (also builds and instantiates the CUDA graph)
     run_iters(args.warmup)
@@ -313,7 +416,7 @@ def main():
         n_conv = sum(1 for n in eng.op_names if eng.op_kinds[n] == "conv")
         roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (all %d launches of one guided-score evaluation)" % n_conv,
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-                "traffic": conv_traffic_bytes(), "traffic_source": conv_traffic_source(),
+                "traffic": conv_traffic()[0], "traffic_source": conv_traffic()[1],
                 "peak_source": pk["source"] + " (sustained)",
                 "avg_launch_ms": conv_ms / n_conv, "share_of_forward": conv_ms / fwd_ms,
                 "algorithmic_flop_per_launch_avg": conv_flop / n_conv,
@@ -328,7 +431,7 @@ def main():
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         lab = labels_host.to(dev, non_blocking=True)                  # H2D from pinned memory
-        samples, nfe = fn(model, weight=1.5, class_labels=lab, rd_seed=seed)   # prior drawn on the CPU and copied H2D inside
+        samples, nfe = fn(model, weight=weight, class_labels=lab, rd_seed=seed)   # prior drawn on the CPU and copied H2D inside
         if world > 1:
             samples = rdd.all_gather_batch(samples, B * world)
         host = samples.cpu()                                           # D2H of the result
@@ -371,26 +474,28 @@ def main():
             hbm = [{"error": repr(e)}]
 
     cpu = None
-    if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        times = cpu_reference_iteration_time(args.ref_batch, 2, 1, threads)
-        ms = 1e3 * sum(times) / len(times)
-        cpu = {"value": args.ref_batch / (ITERS_PER_PASS * ms / 1e3), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle port, batch {args.ref_batch}, 2 PC iterations after 1 warm-up ({ms:.0f} ms each), "
-                         f"extrapolated to 999 iterations; loadavg {os.getloadavg()[0]:.1f}"}
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_c1(20, 5, passes=1)   # bounded sample: one C1 pass (batch 128, 100 steps) on the host cores
+        cpu = {"value": r["B"] / (ITERS_PER_PASS * r["ms"] / 1e3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+               "sample": r["sample"], "batch": r["B"], "c1_pass_seconds": r["c1_pass_seconds"]}
+    eager = None
+    if not args.no_eager_gpu and world == 1:
+        try:
+            torch.cuda.empty_cache()
+            eager = eager_gpu_baseline(dev, B)
+        except Exception as e:   # a side measurement must not take the headline line down
+            eager = {"error": repr(e)}
 
+    config = static_config(B, world)
+    if args.weight != 1.5 or args.per_sample_weight:
+        config["guidance"] = ("per-sample w = %g*U[0,1]" % args.weight) if args.per_sample_weight else ("w = %g" % args.weight)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                       "step": "one PC iteration (2 CFG score evaluations + fused corrector and predictor updates); "
-                               "value = global_batch / (999*ms_per_step + all-gather)",
-                       "l2": "activations of one iteration (>5 GB at 2B=16384) exceed the 126 MB L2; no flush needed",
-                       "noise": "in-kernel Philox", "cuda_graph": True, "all_gather_ms": ag_ms,
-                       "all_samples_inside_cube": inside, "parallelism": f"batch-sharded x{world}, no collective in the loop"},
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config,
+            "run": {"noise": "in-kernel Philox", "cuda_graph": True, "all_gather_ms": ag_ms, "all_samples_inside_cube": inside},
             "clocks": clk, "roofline": roof, "hbm_kernels": {"shape": "[2^20,1,8,9] fp32 (C2)", "peak_GBps": pk["hbm_gbs"],
                                                               "peak_source": pk["source"], "rows": hbm},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_iter * K}
+            "cpu_baseline": cpu, "eager_gpu_baseline": eager, "e2e": e2e, "gpu_launches": launches_per_iter * K}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -163,9 +163,13 @@ int attn_launch(const rd_op_attn& op, cudaStream_t st) {
 namespace rd {
 
 __device__ __forceinline__ float ab_ex2(float x) {
+#ifdef RD_EXACT_ACT  // error-budget builds only (tools/run_errbudget.sh)
+  return exp2f(x);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 constexpr int AB_LD = 72;  // bf16 row stride (144 B): conflict-free 32-bit fragment loads and ldmatrix rows

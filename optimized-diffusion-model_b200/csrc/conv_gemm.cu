@@ -119,9 +119,13 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(const ConvParams& p) 
 // transform costs FFMA + MUFU.TANH + FFMA per channel.  tanh.approx.f32 has 2^-11 relative error, a quarter of the
 // bf16 rounding that follows.
 __device__ __forceinline__ float tanh_approx(float x) {
+#ifdef RD_EXACT_ACT  // error-budget builds only (tools/run_errbudget.sh): libm tanh instead of MUFU.TANH
+  return tanhf(x);
+#else
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 #define RD_TRACE(role, li, pt)                                                                                   \

@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librdb200.so")
+# RDB200_LIB selects a measurement build of the same library (rdb200/build.py `defines`); there is still no fallback
+LIB_PATH = os.environ.get("RDB200_LIB") or os.path.join(_HERE, "librdb200.so")
 
 _lib: Optional[C.CDLL] = None
 

@@ -33,15 +33,19 @@ def _newest_dep() -> float:
     return max(os.path.getmtime(d) for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_dep():
-        return OUT
-    os.makedirs(OBJ, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """`defines` / `out` build a measurement variant next to the product library (e.g. -DRD_EXACT_ACT for the error
+    budget of the approximate SFU functions); the product is always `librdb200.so` with no defines."""
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest_dep():
+        return out
+    obj_dir = OBJ if out == OUT else OBJ + "_" + os.path.basename(out).replace(".so", "")
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = ([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+               ["-c", src, "-o", obj])
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
@@ -51,11 +55,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", out] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
