@@ -156,12 +156,11 @@ def stock_reference_pass(ref, B, N, device, threads=None, weights_seed=0):
     return t1 - t0, stamps + [t1], x
 
 
-def cpu_reference_c1(steps, warmup, passes=3):
+def cpu_reference_c1(steps, warmup, passes=3, B=128, N=100):
     """BASELINE config C1 in full (batch 128, 100 steps, all host threads), `passes` times; the best pass is reported.
     ms_per_step = K consecutive PC iterations of that pass after W warm-up iterations (every iteration does the same
     work).  Falls back to the oracle port when oracle/_ref did not travel (kind says which)."""
     threads = os.cpu_count() or 1
-    B, N = 128, 100
     if _ref_available():
         from oracle import fetch_ref
         if steps + warmup > N - 1:
@@ -178,8 +177,8 @@ def cpu_reference_c1(steps, warmup, passes=3):
                 assert bool(((x >= 0) & (x <= 1)).all())
         ms, total = best
         sample = (f"UNMODIFIED reference (oracle/_ref copy of Reflected-Diffusion, sha-verified), stock "
-                  f"sampling.get_sampling_fn on the CPU, fp32, {threads} threads: BASELINE config C1 in full (batch {B}, "
-                  f"{N} steps, CFG w=1.5) best of {passes} passes = {total:.2f} s per pass; ms_per_step = {steps} consecutive PC "
+                  f"sampling.get_sampling_fn on the CPU, fp32, {threads} threads: BASELINE config C1 (batch {B}, "
+                  f"{N} steps, CFG w=1.5; C1 in full is 128 / 100) best of {passes} passes = {total:.2f} s per pass; ms_per_step = {steps} consecutive PC "
                   f"iterations after {warmup} warm-up iterations of that pass; value extrapolates the per-iteration time to "
                   f"the 999 iterations of the 1000-step sampler; loadavg {os.getloadavg()[0]:.1f}")
         return {"ms": ms, "B": B, "kind": "reference", "cores": threads, "sample": sample, "c1_pass_seconds": total}
@@ -216,7 +215,7 @@ def cpu_reference_c1(steps, warmup, passes=3):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    r = cpu_reference_c1(args.steps, args.warmup)
+    r = cpu_reference_c1(args.steps, args.warmup, passes=args.ref_passes, B=args.ref_batch, N=args.ref_grid)
     value = r["B"] / (ITERS_PER_PASS * r["ms"] / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,6 +291,9 @@ def main():
                     help="strong scaling: total batch split evenly over the GPUs (BASELINE config C4 = 65536)")
     ap.add_argument("--weight", type=float, default=1.5, help="classifier-free guidance weight (C3 sweep)")
     ap.add_argument("--per-sample-weight", action="store_true", help="w_b = weight * U[0,1] per sample (run_train.py:173)")
+    ap.add_argument("--ref-batch", type=int, default=128, help="reference arm: batch (C1 = 128)")
+    ap.add_argument("--ref-grid", type=int, default=100, help="reference arm: sampler grid points (C1 = 100)")
+    ap.add_argument("--ref-passes", type=int, default=3, help="reference arm: passes, best one reported")
     ap.add_argument("--no-eager-gpu", action="store_true", help="skip the stock-reference-on-this-GPU baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

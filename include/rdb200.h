@@ -19,11 +19,14 @@
  *   rd_plan_* / rd_op         NCSNpp.forward and its layers        models/ncsnpp.py:226-354,
  *                                                                  models/layerspp.py:67-214, models/layers.py:531-540
  *   rd_sampler_*              get_pc_sampler / pc_sampler loop     sampling.py:292-339
+ *   rd_checksum_f32           (no counterpart: the reference re-reads nn.Parameters on every call; packed kernel
+ *                             weights must notice ema.copy_to / restore, models/ema.py:60-88)
  * "next" rows (callers either side of the path):
  *   rd_perturb_reflect_f32    x_t = cube.reflect(mean + std z)      losses.py:80-82
  *   rd_dsm_reduce_f32         weighted squared error + reduce_op    losses.py:86-92
  *   rd_pf_drift_f32           probability-flow drift * mollifier    sampling.py:345-383, sde_lib.py:93-101
  *   rd_gto_halo_decode_f32    latent -> physical units              ../Benchmark/gto_halo_benchmarking.py:255-328, 335-363
+ *   rd_gto_halo_encode_f32    dataset row -> latent                 datasets.py:82-98 (GTOHaloImageDataset.__getitem__)
  */
 #ifndef RDB200_H
 #define RDB200_H
@@ -118,6 +121,11 @@ typedef struct rd_gto_halo_codec {
 int rd_gto_halo_decode_f32(const float* latents, float* out, size_t n, size_t row_stride,
                            const rd_gto_halo_codec* codec, void* stream);
 
+/* dataset rows -> latents (datasets.py:82-98): raw [n, n_in] fp32 is zero-padded to n_latent values per sample and
+ * every entry z-scored ((v - mean) / std, padding included); labels (optional) [n] receives the un-normalised first value. */
+int rd_gto_halo_encode_f32(const float* raw, float* latents, float* labels, size_t n, size_t n_in, size_t n_latent,
+                           float data_mean, float data_std, void* stream);
+
 /* ---------------------------------------------------------------- NCSN++ forward as an op plan */
 /* The host (python, mirroring NCSNpp.__init__) lowers the network to a flat list of ops over
  * device buffers; the library owns only the kernels.  Activations are NHWC bf16. */
@@ -131,8 +139,15 @@ enum rd_op_kind {
   RD_OP_ATTN_BLOCK = 6 /* whole AttnBlockpp fused: GN, q/k/v, softmax(qk^T)v, output projection, skip */
 };
 
+/* Precision of the network plan (every op of a plan uses the same one):
+ *   RD_PREC_BF16   bf16 NHWC activations, bf16 MMA operands, fp32 accumulation / statistics / epilogues
+ *   RD_PREC_F32X3  "fp32-class": fp32 NHWC activations, operands split into bf16 hi + lo, three tcgen05 MMAs per k-step
+ *                  (the reference is fp32 end to end, layers.py:103-109) */
+#define RD_PREC_BF16 0
+#define RD_PREC_F32X3 1
+
 typedef struct rd_conv_src {
-  const void* ptr; /* bf16 NHWC [B2, Hs, Ws, C] */
+  const void* ptr; /* NHWC [B2, Hs, Ws, C], bf16 (fp32 when precision == RD_PREC_F32X3) */
   int32_t C;       /* channels of this source (multiple of 8; the total over sources a multiple of 64) */
   int32_t Hs, Ws;  /* stored spatial size; gathered to (H_in, W_in) by nearest mapping */
 } rd_conv_src;
@@ -145,28 +160,33 @@ typedef struct rd_op_conv {
   int32_t stride;             /* 1 or 2 (2 only with pad == 0: Downsample)              */
   int32_t H_out, W_out;
   int32_t ntaps;              /* 9 (3x3 conv) or 1 (1x1: NIN / attention projections)   */
-  int32_t C_out;              /* N of the GEMM: multiple of 32, <= 256                  */
+  int32_t C_out;              /* N of the GEMM (this launch): multiple of 32, <= 256    */
   int32_t gn_groups;          /* 0: no GroupNorm/SiLU prologue                          */
   int32_t gn_silu;            /* 1: SiLU after GN (ResBlock), 0: GN only (attention)    */
   float gn_eps;
   const float* gn_gamma;      /* [C_in_total] */
   const float* gn_beta;
-  const void* w;              /* bf16 packed [C_in/64][ntaps][8][C_out][8] (rdb200/pack.py) */
+  const void* w;              /* bf16 packed [C_in/64][ntaps][8][C_out][8] (rdb200/pack.py); F32X3: [C_in/64][ntaps][hi|lo][8][C_out][8] */
   const float* bias;          /* [C_out] (sum of all fused biases) */
   const float* tproj;         /* [B2, tproj_stride] per-sample additive term or NULL */
   int32_t tproj_stride, tproj_off;
   int32_t tproj_wrap;         /* >0: samples with index > tproj_wrap read row tproj_wrap (shared unconditional CFG row) */
-  const void* residual;       /* bf16 NHWC [B2,H_out,W_out,C_out] identity skip or NULL */
+  const void* residual;       /* NHWC [B2,H_out,W_out,out_stride] identity skip or NULL (same dtype as out) */
   float out_scale;            /* 1/sqrt(2) when skip_rescale, else 1 */
-  void* out;                  /* bf16 NHWC [B2,H_out,W_out,C_out] */
+  void* out;                  /* NHWC [B2,H_out,W_out,out_stride], bf16 or fp32 by `precision` */
   int32_t B2;                 /* samples (2B under CFG) */
   int32_t samples_per_cta;    /* 0: library picks the tile geometry; >0: planner override */
+  int32_t precision;          /* RD_PREC_* */
+  int32_t out_stride;         /* 0 = C_out; otherwise channels per pixel of out / residual: a layer wider than one launch
+                                 (C_out > 256, or a tile geometry that does not fit) is issued as channel slices, each
+                                 with out / residual / bias / tproj_off / w advanced to its first channel */
 } rd_op_conv;
 
 typedef struct rd_op_attn {
-  const void* qkv; /* bf16 [B2, T, 3C] (q | k | v) */
-  void* out;       /* bf16 [B2, T, C] */
+  const void* qkv; /* [B2, T, 3C] (q | k | v), bf16 or fp32 by `precision` */
+  void* out;       /* [B2, T, C] */
   int32_t B2, T, C;
+  int32_t precision; /* RD_PREC_* */
 } rd_op_attn;
 
 typedef struct rd_op_attn_block {
@@ -198,12 +218,13 @@ typedef struct rd_op_inconv {
   const float* x;    /* fp32 [B, C_in, H, W] (NCHW state, C_in small) ; sample b2 reads x[b2 % B] */
   const float* w;    /* fp32 [C_out, C_in, 3, 3] */
   const float* bias; /* [C_out] */
-  void* out;         /* bf16 NHWC [B2,H,W,C_out] */
+  void* out;         /* NHWC [B2,H,W,C_out], bf16 or fp32 by `precision` */
   int32_t B, B2, C_in, C_out, H, W;
+  int32_t precision; /* RD_PREC_* */
 } rd_op_inconv;
 
 typedef struct rd_op_outhead {
-  const void* h;       /* bf16 NHWC [B2,H,W,C] */
+  const void* h;       /* NHWC [B2,H,W,C], bf16 or fp32 by `precision` */
   const float* gamma;  /* out_norm */
   const float* beta;
   const float* w;      /* fp32 [C_img, C, 3, 3] out_conv.weight */
@@ -213,6 +234,9 @@ typedef struct rd_op_outhead {
   float* score;        /* fp32 [B, C_img, H, W] guided score (or [B2,...] raw if cfg == 0) */
   int32_t B, B2, C, C_img, H, W, groups, cfg;
   float eps;
+  int32_t precision;   /* RD_PREC_* */
+  const float* sigma_table; /* NULL, or (model.scale_by_sigma, ncsnpp.py:350-351) the score is divided by sigma: */
+  const int32_t* step_ctr;  /*   sigma_table[*step_ctr] when step_ctr != NULL (sampler), else sigma_table[b2] per sample */
 } rd_op_outhead;
 
 typedef struct rd_op {
@@ -238,8 +262,13 @@ int rd_plan_run_range(rd_plan* p, int first, int count, void* stream);
 int rd_plan_destroy(rd_plan* p);
 /* shared-memory bytes / CTAs a conv op will launch with (planner feedback, also validates the op) */
 int rd_conv_launch_info(const rd_op_conv* op, int* smem_bytes, int* grid, int* rows_alloc);
-/* developer aid: CTA 0 of subsequent conv launches records clock64() stamps [3 roles][groups][8 points] into buf (NULL disables) */
-int rd_conv_set_trace(long long* buf, int groups);
+
+/* ---------------------------------------------------------------- parameter change detection */
+/* 64-bit content checksum of a set of fp32 device tensors (value AND position of every element enter the sum), so the
+ * host can tell with one launch + 8 bytes of D2H whether parameters were rewritten in place (EMA copy_to / restore,
+ * load_state_dict; reference models/ema.py:60-88).  segs: device [n_segs][3] int64 = (address, index of the first
+ * element in the concatenation of all tensors, element count); out: device uint64. */
+int rd_checksum_f32(const int64_t* segs, int n_segs, uint64_t* out, void* stream);
 
 /* ---------------------------------------------------------------- whole sampler (sampling.py:292-339) */
 typedef struct rd_sampler_desc {

@@ -1,19 +1,19 @@
-// attn_core.cu -- softmax(q k^T / sqrt(C)) v for the single-head pixel attention of AttnBlockpp
-// (reference models/layerspp.py:87-91), one CTA per sample, T = H*W tokens (72 / 81 for GTO-Halo),
-// C = 64 channels.  q/k/v come from the fused qkv projection (conv_gemm.cu, N = 3C) as bf16
-// [B2, T, 3C]; the output feeds the NIN_3 projection kernel.
+// attn_core.cu -- the single-head pixel attention of AttnBlockpp (reference models/layerspp.py:80-96).
 //
-// Round-1 implementation: register-resident flash-style kernel on mma.sync.m16n8k16 (bf16 in,
-// fp32 accumulate, fp32 softmax).  It is ~3 % of the network's FLOPs; the projections around it
-// (11.8 of the 18.4 MFLOP per attention-bearing sample) already run on tcgen05.  Moving QK^T / PV
-// to tcgen05 (M=128 tile per sample, S in TMEM) is the planned follow-up.
+//   attn_block_kernel   the whole block (GroupNorm, q/k/v NIN, softmax(q k^T / sqrt(C)) v, output NIN, skip / sqrt 2) in ONE
+//                       launch for the GTO-Halo shapes (C = 64, T <= 128 tokens, bf16 plan): mma.sync m16n8k16, activations
+//                       never leave the SM.
+//   attn_core_kernel    softmax(q k^T / sqrt(C)) v alone, for any C (multiple of 64) and any T, bf16 or fp32 I/O, fp32 math:
+//                       the attention core of the fp32-class plan (its q/k/v and output projections run on tcgen05 in
+//                       conv_gemm.cu with split-bf16 operands) and of shapes the fused kernel does not cover (BASELINE
+//                       config C5: T = 256 tokens, C = 256).  Flash-style: 64 queries x 64 keys per step, online softmax.
 #include "rd_common.h"
 #include <cuda_bf16.h>
+#include <type_traits>
 
 namespace rd {
 
 constexpr int ATT_C = 64;
-constexpr int ATT_LD = 72;  // smem row stride in bf16 (144 B): conflict-free fragment loads
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -27,128 +27,182 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// T16 = number of 16-key blocks (keys padded to 16*T16)
-template <int T16>
-__global__ void __launch_bounds__(32 * T16) attn_core_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                             __nv_bfloat16* __restrict__ out, int T, float scale) {
-  constexpr int TP = 16 * T16;
-  __shared__ __align__(16) __nv_bfloat16 Ks[TP * ATT_LD];
-  __shared__ __align__(16) __nv_bfloat16 Vs[TP * ATT_LD];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * T * (3 * ATT_C);
+// ---------------------------------------------------------------------------------------------------------------------
+// attn_core_kernel: grid (B2, ceil(T/64)), 256 threads.  Thread (ty, tx) = (tid / 16, tid % 16) owns query rows
+// 4*ty .. 4*ty+3 of the CTA's 64-query tile; in the score tile it owns keys 4*tx .. 4*tx+3, in the output it owns
+// channels 64*cc + 4*tx .. +3 of every 64-channel chunk cc.  Operands are staged per 64-channel chunk as fp32
+// [k][row] images (row stride 68 floats: aligned float4 reads, both operands of the inner product broadcast along one
+// thread-grid axis), so shared memory is 64 KB whatever C is.  The 16 threads that share a query row are the 16 lanes
+// of a half-warp: row maxima / sums are xor-shuffles.
+constexpr int AC_BQ = 64, AC_BK = 64, AC_LD = 68;
 
-  // stage K and V (zero rows beyond T)
-  for (int i = tid; i < TP * 16; i += blockDim.x) {
-    const int row = i >> 4, seg = i & 15;  // seg 0-7: K chunks, 8-15: V chunks
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < T) v = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(row) * (3 * ATT_C) + ATT_C + seg * 8);
-    __nv_bfloat16* dst = (seg < 8 ? Ks : Vs) + row * ATT_LD + (seg & 7) * 8;
-    *reinterpret_cast<uint4*>(dst) = v;
-  }
-  __syncthreads();
-
-  const int g = lane >> 2, q4 = lane & 3;
-  const int r0 = warp * 16 + g, r1 = r0 + 8;
-  const int r0c = min(r0, T - 1), r1c = min(r1, T - 1);
-  // Q fragments: 4 k-steps of 16 channels
-  uint32_t qa[4][4];
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const __nv_bfloat16* q0 = base + static_cast<size_t>(r0c) * (3 * ATT_C) + kk * 16 + 2 * q4;
-    const __nv_bfloat16* q1 = base + static_cast<size_t>(r1c) * (3 * ATT_C) + kk * 16 + 2 * q4;
-    qa[kk][0] = *reinterpret_cast<const uint32_t*>(q0);
-    qa[kk][1] = *reinterpret_cast<const uint32_t*>(q1);
-    qa[kk][2] = *reinterpret_cast<const uint32_t*>(q0 + 8);
-    qa[kk][3] = *reinterpret_cast<const uint32_t*>(q1 + 8);
-  }
-  // S = Q K^T
-  float s[2 * T16][4];
-#pragma unroll
-  for (int nb = 0; nb < 2 * T16; ++nb) {
-    s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.0f;
-    const __nv_bfloat16* kr = Ks + (nb * 8 + g) * ATT_LD + 2 * q4;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + kk * 16);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8);
-      mma_bf16_16816(s[nb], qa[kk], b0, b1);
-    }
-  }
-  // softmax over the T valid keys (rows r0: elements [0],[1]; r1: [2],[3]; key = nb*8 + 2*q4 + {0,1})
-  float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-  for (int nb = 0; nb < 2 * T16; ++nb) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const bool ok = (nb * 8 + 2 * q4 + e) < T;
-      s[nb][e] = ok ? s[nb][e] * scale : -INFINITY;
-      s[nb][2 + e] = ok ? s[nb][2 + e] * scale : -INFINITY;
-      m0 = fmaxf(m0, s[nb][e]);
-      m1 = fmaxf(m1, s[nb][2 + e]);
-    }
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  float l0 = 0.0f, l1 = 0.0f;
-#pragma unroll
-  for (int nb = 0; nb < 2 * T16; ++nb) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      s[nb][e] = __expf(s[nb][e] - m0);
-      s[nb][2 + e] = __expf(s[nb][2 + e] - m1);
-      l0 += s[nb][e];
-      l1 += s[nb][2 + e];
-    }
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-
-  // O = P V : k-steps of 16 keys, 8 output n-blocks of 8 channels
-  float o[ATT_C / 8][4];
-#pragma unroll
-  for (int nb = 0; nb < ATT_C / 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.0f;
-#pragma unroll
-  for (int kk = 0; kk < T16; ++kk) {
-    uint32_t pa[4];
-    pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-    pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-    pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-    for (int nb = 0; nb < ATT_C / 8; ++nb) {
-      // B fragment (16 keys x 8 channels) from row-major V via ldmatrix.trans
-      uint32_t b0, b1;
-      const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(Vs + (kk * 16 + (lane & 15)) * ATT_LD + nb * 8));
-      asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
-      mma_bf16_16816(o[nb], pa, b0, b1);
-    }
-  }
-  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-  __nv_bfloat16* ob = out + static_cast<size_t>(b) * T * ATT_C;
-#pragma unroll
-  for (int nb = 0; nb < ATT_C / 8; ++nb) {
-    if (r0 < T) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r0) * ATT_C + nb * 8 + 2 * q4) = pack_bf16(o[nb][0] * i0, o[nb][1] * i0);
-    if (r1 < T) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r1) * ATT_C + nb * 8 + 2 * q4) = pack_bf16(o[nb][2] * i1, o[nb][3] * i1);
+template <typename T>
+__device__ __forceinline__ float4 ac_load4(const T* p) {
+  if constexpr (std::is_same<T, float>::value) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+  } else {
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
   }
 }
 
-int attn_launch(const rd_op_attn& op, cudaStream_t st) {
-  RD_REQUIRE(op.qkv && op.out && op.B2 > 0, "attn: null pointer / empty batch");
-  RD_REQUIRE(op.C == ATT_C, "attn: only C == %d is supported in this round (got %d)", ATT_C, op.C);
-  RD_REQUIRE(op.T >= 1 && op.T <= 128, "attn: T must be in [1,128] (got %d)", op.T);
-  const float scale = 1.0f / sqrtf(static_cast<float>(op.C));  // int(C) ** (-0.5)
-  const __nv_bfloat16* qkv = static_cast<const __nv_bfloat16*>(op.qkv);
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(op.out);
-  const int t16 = (op.T + 15) / 16;
-  switch (t16) {
-#define RD_ATT_CASE(n) \
-  case n: attn_core_kernel<n><<<op.B2, 32 * n, 0, st>>>(qkv, out, op.T, scale); break;
-    RD_ATT_CASE(1) RD_ATT_CASE(2) RD_ATT_CASE(3) RD_ATT_CASE(4) RD_ATT_CASE(5) RD_ATT_CASE(6) RD_ATT_CASE(7) RD_ATT_CASE(8)
-#undef RD_ATT_CASE
-    default: return fail(RD_E_UNSUPPORTED, "attn: T=%d unsupported", op.T);
+template <typename T, int NCC>  // NCC = C / 64
+__global__ void __launch_bounds__(256) attn_core_kernel(const T* __restrict__ qkv, T* __restrict__ out, int Tn, float scale) {
+  constexpr int C = 64 * NCC;
+  extern __shared__ __align__(16) float ac_smem[];
+  float* Qt = ac_smem;               // [64 k][AC_LD] query chunk, transposed
+  float* Kt = Qt + 64 * AC_LD;       // [64 k][AC_LD] key chunk, transposed
+  float* Pt = Kt + 64 * AC_LD;       // [64 keys][AC_LD] probabilities, transposed
+  float* Vs = Pt + 64 * AC_LD;       // [64 keys][AC_LD] value chunk, row-major
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int q0 = blockIdx.y * AC_BQ;
+  const T* base = qkv + static_cast<size_t>(blockIdx.x) * Tn * (3 * C);
+  // loader mapping: 16 consecutive threads read the 64 contiguous channels of one row
+  const int lk = (tid & 15) * 4, lr = tid >> 4;
+  auto stage_t = [&](float* dst, int row0, int col0) {  // dst[k][row] <- tensor[row0 + row][col0 + k], zero beyond T
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = lr + 16 * j;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < Tn) v = ac_load4(base + static_cast<size_t>(row0 + r) * (3 * C) + col0 + lk);
+      dst[(lk + 0) * AC_LD + r] = v.x; dst[(lk + 1) * AC_LD + r] = v.y;
+      dst[(lk + 2) * AC_LD + r] = v.z; dst[(lk + 3) * AC_LD + r] = v.w;
+    }
+  };
+  float o[NCC][4][4];
+#pragma unroll
+  for (int cc = 0; cc < NCC; ++cc)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[cc][i][j] = 0.0f;
+  float m[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.0f; }
+
+  for (int k0 = 0; k0 < Tn; k0 += AC_BK) {
+    // ---- S = Q K^T over the channel chunks
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.0f;
+    for (int cc = 0; cc < NCC; ++cc) {
+      __syncthreads();  // previous readers of Qt / Kt (and of Pt / Vs from the last key tile) are done
+      stage_t(Qt, q0, cc * 64);
+      stage_t(Kt, k0, C + cc * 64);
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(Qt + k * AC_LD + 4 * ty);
+        const float4 b = *reinterpret_cast<const float4*>(Kt + k * AC_LD + 4 * tx);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[i][j] = fmaf(av[i], bv[j], s[i][j]);
+      }
+    }
+    // ---- online softmax (keys beyond T masked)
+    float alpha[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = (k0 + 4 * tx + j < Tn) ? s[i][j] * scale : -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      const float mn = fmaxf(m[i], mx);  // finite: every key tile holds at least one valid key
+      alpha[i] = expf(m[i] - mn);        // exp(-inf) = 0 on the first tile
+      float rs = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[i][j] = expf(s[i][j] - mn); rs += s[i][j]; }
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, d);
+      l[i] = fmaf(l[i], alpha[i], rs);
+      m[i] = mn;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(Pt + (4 * tx + j) * AC_LD + 4 * ty) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+    // ---- O = alpha O + P V over the channel chunks
+#pragma unroll
+    for (int cc = 0; cc < NCC; ++cc) {
+      __syncthreads();  // Pt complete (first chunk) / previous chunk's readers of Vs done
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = lr + 16 * j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + r < Tn) v = ac_load4(base + static_cast<size_t>(k0 + r) * (3 * C) + 2 * C + cc * 64 + lk);
+        *reinterpret_cast<float4*>(Vs + r * AC_LD + lk) = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[cc][i][j] *= alpha[i];
+#pragma unroll 8
+      for (int k = 0; k < 64; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(Pt + k * AC_LD + 4 * ty);
+        const float4 b = *reinterpret_cast<const float4*>(Vs + k * AC_LD + 4 * tx);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[cc][i][j] = fmaf(av[i], bv[j], o[cc][i][j]);
+      }
+    }
   }
+  T* ob = out + static_cast<size_t>(blockIdx.x) * Tn * C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = q0 + 4 * ty + i;
+    if (row >= Tn) continue;
+    const float inv = 1.0f / l[i];
+#pragma unroll
+    for (int cc = 0; cc < NCC; ++cc) {
+      T* dst = ob + static_cast<size_t>(row) * C + cc * 64 + 4 * tx;
+      if constexpr (std::is_same<T, float>::value) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[cc][i][0] * inv, o[cc][i][1] * inv, o[cc][i][2] * inv, o[cc][i][3] * inv);
+      } else {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(o[cc][i][0] * inv, o[cc][i][1] * inv), pack_bf16(o[cc][i][2] * inv, o[cc][i][3] * inv));
+      }
+    }
+  }
+}
+
+template <typename T, int NCC>
+static int attn_core_launch_t(const rd_op_attn& op, cudaStream_t st, float scale) {
+  constexpr int smem = 4 * 64 * AC_LD * 4;
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attn_core_kernel<T, NCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "attn: %s", cudaGetErrorString(e));
+    configured[dev] = true;
+  }
+  dim3 grid(op.B2, (op.T + AC_BQ - 1) / AC_BQ);
+  attn_core_kernel<T, NCC><<<grid, 256, smem, st>>>(static_cast<const T*>(op.qkv), static_cast<T*>(op.out), op.T, scale);
   return check_launch("attn_core_kernel");
+}
+
+int attn_launch(const rd_op_attn& op, cudaStream_t st) {
+  RD_REQUIRE(op.qkv && op.out && op.B2 > 0 && op.T >= 1, "attn: null pointer / empty batch");
+  RD_REQUIRE(op.precision == RD_PREC_BF16 || op.precision == RD_PREC_F32X3, "attn: unknown precision %d", op.precision);
+  const float scale = 1.0f / sqrtf(static_cast<float>(op.C));  // int(C) ** (-0.5)
+  const bool f32 = op.precision == RD_PREC_F32X3;
+  switch (op.C) {
+    case 64: return f32 ? attn_core_launch_t<float, 1>(op, st, scale) : attn_core_launch_t<__nv_bfloat16, 1>(op, st, scale);
+    case 128: return f32 ? attn_core_launch_t<float, 2>(op, st, scale) : attn_core_launch_t<__nv_bfloat16, 2>(op, st, scale);
+    case 256: return f32 ? attn_core_launch_t<float, 4>(op, st, scale) : attn_core_launch_t<__nv_bfloat16, 4>(op, st, scale);
+    default: return fail(RD_E_UNSUPPORTED, "attn: C=%d unsupported (64, 128 or 256)", op.C);
+  }
 }
 
 }  // namespace rd
@@ -471,7 +525,10 @@ int attn_block_launch(const rd_op_attn_block& op, cudaStream_t st) {
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(op.out);
   const __nv_bfloat16* wq = static_cast<const __nv_bfloat16*>(op.wqkv_t);
   const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(op.wproj_t);
-  static bool configured[9] = {};
+  static bool configured_dev[64][9] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  bool* configured = configured_dev[dev];
   switch (t16) {
 #define RD_AB_CASE(n)                                                                                                              \
   case n:                                                                                                                           \

@@ -27,6 +27,11 @@
 //     address advanced by (dy*Wp+dx)*16 B: nine taps, no im2col, no data movement (validated on B200 by
 //     tools/probe_umma.cu).  Outputs at padding rows are computed and dropped.
 //   * All index arithmetic is group-invariant and tabulated once per CTA in shared memory.
+//   * Two precisions (template parameter X3).  bf16: bf16 NHWC activations, one MMA per k-step.  fp32-class ("x3"):
+//     fp32 NHWC activations; both operands are split into bf16 hi + bf16 lo (x = hi + lo to 2^-17) and every k-step
+//     issues lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator (tools/probe_split.cu: 5e-6 .. 1e-5 of the
+//     output range against fp64 for K = 576 .. 2304, i.e. better than the TF32 convolutions the reference runs by
+//     default on a GPU); GroupNorm / SiLU / bias / temb / skip stay in fp32 and SiLU uses libm tanh.
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -51,7 +56,7 @@ constexpr int GNM_CPG4 = 2;     // 4 channels per group: two groups per item
 constexpr int GNM_GENERAL = 3;  // anything else (192 channels / 32 groups = 6)
 
 struct ConvParams {
-  const __nv_bfloat16* src[2];
+  const void* src[2];  // bf16 (or fp32 when x3) NHWC
   int C[2], Hs[2], Ws[2];
   int nsrc;
   int H, W;          // logical (gathered) input image
@@ -62,15 +67,14 @@ struct ConvParams {
   int ntaps;         // 9 or 1
   int Cin, KC;       // total input channels, Cin/8
   int nchunks;       // Cin/64
-  int N;             // C_out
+  int N;             // C_out of this launch (GEMM N)
+  int out_stride;    // channels per pixel of `out` / `residual` (>= N: the launch may write a channel slice)
+  int x3;            // fp32-class mode: fp32 activations, split-bf16 operands, three MMAs per k-step
   int S, n_tiles, R; // samples per group, 128-row accumulator tiles, staged rows (odd)
   int n_groups;
   int a_stages, a_stage_bytes;
   int w_resident, w_stages, w_slab_bytes, n_slabs;
   int acc_bufs;
-  int n_issuers;     // MMA-issuing warps (tiles are dealt round-robin)
-  int w_reps;        // identical copies of the packed filter, n_slabs*w_slab_bytes apart; CTA i reads copy i % w_reps
-  int cluster;       // CTAs per thread-block cluster sharing the streamed filter by TMA multicast (1 = no cluster)
   int xmode, rc_PS;  // transform mode: >0 = register-cached single pass (value = register slots, rc_PS pixel slices), 0 = streaming
   int gnm;
   int tmem_cols;     // power of two >= acc_bufs*n_tiles*N
@@ -78,17 +82,14 @@ struct ConvParams {
   float eps;
   const float* gamma;
   const float* beta;
-  const __nv_bfloat16* w;  // [nchunks][ntaps][8][N][8]
+  const __nv_bfloat16* w;  // [nchunks][ntaps][8][N][8]   (x3: [nchunks][ntaps][hi|lo][8][N][8])
   const float* bias;
   const float* tproj;
   int tproj_stride, tproj_off, tproj_wrap;
-  const __nv_bfloat16* residual;
+  const void* residual;
   float out_scale;
-  __nv_bfloat16* out;
+  void* out;
   int B2;
-  long long* trace;  // optional clock64 trace buffer (CTA 0 only): [role 0..2][group li][point 0..7]
-  int trace_groups;
-  int debug;  // RD_CONV_DEBUG bit 0: skip transform work, bit 1: skip epilogue work, bit 2: skip MMAs (timing experiments only)
   unsigned char ymap[2][MAX_HW], xmap[2][MAX_HW];
 };
 
@@ -128,11 +129,6 @@ __device__ __forceinline__ float tanh_approx(float x) {
 #endif
 }
 
-#define RD_TRACE(role, li, pt)                                                                                   \
-  do {                                                                                                          \
-    if (p.trace && blockIdx.x == 0 && (li) < p.trace_groups) p.trace[((role) * p.trace_groups + (li)) * 8 + (pt)] = clock64(); \
-  } while (0)
-
 // Programmatic dependent launch: the next conv launch of the stream may start its prologue (barriers, TMEM, index
 // tables, operand-ring zeroing, filter fetch) on SMs this grid has already left; it must not touch activations
 // before pdl_wait() (= the previous grid has completed and its writes are visible).
@@ -165,17 +161,27 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // constant so that no MMA is predicated: with run-time tile counts ptxas re-materialises the (zero, idesc) and
 // descriptor-high uniform-register pairs for every instruction, and the single issuing thread -- whose uniform-
 // datapath instructions cost ~10 cycles each -- drops from the tensor core's 50 cycles per MMA to 70.
-template <int NT, bool TILE_OUTER>
+template <int NT, bool TILE_OUTER, bool X3>
 __device__ __forceinline__ void issue_tap(uint32_t acc, uint32_t N, uint32_t a_lo, uint32_t w_lo, uint32_t kstep_a,
-                                          uint32_t kstep_w, uint64_t desc_hi, uint32_t idesc, uint32_t accum) {
+                                          uint32_t kstep_w, uint64_t desc_hi, uint32_t idesc, uint32_t accum,
+                                          uint32_t a_half, uint32_t w_half) {
+  // one k-step of one tile: a single MMA, or (x3) the three split-bf16 terms, small ones first
+  auto kstep = [&](uint32_t d, uint32_t a, uint32_t w, uint32_t acc_flag) {
+    if (X3) {
+      umma_bf16_ss(d, desc_hi | (a + a_half), desc_hi | w, idesc, acc_flag);  // lo * hi
+      umma_bf16_ss(d, desc_hi | a, desc_hi | (w + w_half), idesc, 1u);        // hi * lo
+      umma_bf16_ss(d, desc_hi | a, desc_hi | w, idesc, 1u);                   // hi * hi
+    } else {
+      umma_bf16_ss(d, desc_hi | a, desc_hi | w, idesc, acc_flag);
+    }
+  };
   if (!TILE_OUTER) {
     // narrow N: the tiles of one k-step together (they share the B descriptor)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const uint64_t db = desc_hi | (w_lo + kk * kstep_w);
-      const uint32_t a_k = a_lo + kk * kstep_a;
+      const uint32_t a_k = a_lo + kk * kstep_a, w_k = w_lo + kk * kstep_w;
 #pragma unroll
-      for (int t = 0; t < NT; ++t) umma_bf16_ss(acc + t * N, desc_hi | (a_k + t * 128), db, idesc, kk == 0 ? accum : 1u);
+      for (int t = 0; t < NT; ++t) kstep(acc + t * N, a_k + t * 128, w_k, kk == 0 ? accum : 1u);
     }
   } else {
     // N >= 128: the four k-steps of a tile back to back on the same accumulator (65 vs 86 cycles per MMA on
@@ -183,9 +189,7 @@ __device__ __forceinline__ void issue_tap(uint32_t acc, uint32_t N, uint32_t a_l
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16_ss(acc + t * N, desc_hi | (a_lo + t * 128 + kk * kstep_a), desc_hi | (w_lo + kk * kstep_w), idesc,
-                     kk == 0 ? accum : 1u);
+      for (int kk = 0; kk < 4; ++kk) kstep(acc + t * N, a_lo + t * 128 + kk * kstep_a, w_lo + kk * kstep_w, kk == 0 ? accum : 1u);
     }
   }
 }
@@ -228,26 +232,79 @@ __device__ __forceinline__ void epi_finish_block(const uint32_t (&v)[32], const 
 // block are requested before the current block is converted (two register sets, no copies).
 template <bool RES>
 __device__ __forceinline__ void epi_row(uint32_t tacc, int N, const float* __restrict__ btr, float oscale,
-                                        const __nv_bfloat16* __restrict__ rrow, __nv_bfloat16* orow, bool valid, bool skip_ld) {
+                                        const __nv_bfloat16* __restrict__ rrow, __nv_bfloat16* orow, bool valid) {
   u32x8 ra[2], rb[2];
   if (RES && valid) { ra[0] = ld_global_256(rrow); ra[1] = ld_global_256(rrow + 16); }
   for (int c0 = 0; c0 < N; c0 += 64) {
     uint32_t v[32];
-    if (!skip_ld) tmem_ld32(tacc + c0, v);
+    tmem_ld32(tacc + c0, v);
     if (RES && valid && c0 + 32 < N) { rb[0] = ld_global_256(rrow + c0 + 32); rb[1] = ld_global_256(rrow + c0 + 48); }
-    if (!skip_ld) tmem_ld_wait32(v);
+    tmem_ld_wait32(v);
     if (valid) epi_finish_block<RES>(v, btr + c0, oscale, ra, orow + c0);
     if (c0 + 32 < N) {
-      if (!skip_ld) tmem_ld32(tacc + c0 + 32, v);
+      tmem_ld32(tacc + c0 + 32, v);
       if (RES && valid && c0 + 64 < N) { ra[0] = ld_global_256(rrow + c0 + 64); ra[1] = ld_global_256(rrow + c0 + 80); }
-      if (!skip_ld) tmem_ld_wait32(v);
+      tmem_ld_wait32(v);
       if (valid) epi_finish_block<RES>(v, btr + c0 + 32, oscale, rb, orow + c0 + 32);
     }
   }
 }
 
-template <int GNM, int RC>
+// fp32-class epilogue: the same row walk with fp32 residual / output (128 bytes per 32-column block and thread).
+template <bool RES>
+__device__ __forceinline__ void epi_row_f32(uint32_t tacc, int N, const float* __restrict__ btr, float oscale,
+                                            const float* __restrict__ rrow, float* orow, bool valid) {
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tacc + c0, v);
+    u32x8 r[4];
+    if (RES && valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = ld_global_256(rrow + c0 + 8 * j);
+    }
+    tmem_ld_wait32(v);
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 b0 = *reinterpret_cast<const float4*>(btr + c0 + 8 * j), b1 = *reinterpret_cast<const float4*>(btr + c0 + 8 * j + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        u32x8 t;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float a = fmaf(__uint_as_float(v[8 * j + e]), oscale, bb[e]);
+          if (RES) a = fmaf(__uint_as_float(r[j].v[e]), oscale, a);
+          t.v[e] = __float_as_uint(a);
+        }
+        st_global_256(orow + c0 + 8 * j, t);
+      }
+    }
+  }
+}
+
+// x ~= hi + lo with both halves bf16 (round to nearest): |x - hi - lo| <= 2^-17 |x|
+__device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    const float2 hf = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void ldg8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <int GNM, int RC, bool X3>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!X3 || RC == 0, "the fp32-class mode uses the streaming transform");
+  using act_t = typename std::conditional<X3, float, __nv_bfloat16>::type;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar_a_full[MAX_A_STAGES], bar_a_empty[MAX_A_STAGES];
   __shared__ uint64_t bar_w_full[MAX_W_STAGES], bar_w_empty[MAX_W_STAGES];
@@ -271,20 +328,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = p.H * p.W;
-  // Clustered launches walk the filter ring in lock step, so every CTA runs the same number of rounds; a round
-  // whose group index is past the end is a dummy (no samples: S_act <= 0, nothing staged, nothing stored).
-  const int my_groups = p.cluster > 1 ? (p.n_groups + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
-                        : (p.n_groups > static_cast<int>(blockIdx.x))
+  const int my_groups = (p.n_groups > static_cast<int>(blockIdx.x))
                             ? (p.n_groups - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
                             : 0;
-  const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0;
-  const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1);
 
   // ------------------------------------------------------------------ setup
   if (tid == 0) {
-    for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], p.n_issuers); }
-    for (int i = 0; i < MAX_W_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], p.n_issuers * p.cluster); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], p.n_issuers); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
+    for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], 1); }
+    for (int i = 0; i < MAX_W_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
@@ -306,12 +358,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       oy = Y >> 1; ox = X >> 1;
     }
     valid = valid && oy < p.Ho && ox < p.Wo;
-    t_orow[row] = valid ? ((s * p.Ho + oy) * p.Wo + ox) * p.N : -1;
+    t_orow[row] = valid ? ((s * p.Ho + oy) * p.Wo + ox) * p.out_stride : -1;
     t_os[row] = static_cast<unsigned char>(valid ? s : 0);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();  // peers' barriers must be initialised before anything is multicast to them
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
@@ -324,18 +375,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     const bool leader = elect_one();
     const int N = p.N, ntaps = p.ntaps, nchunks = p.nchunks, Wp = p.Wp;
     const int a_stages = p.a_stages, w_stages = p.w_stages, acc_bufs = p.acc_bufs;
-    const bool w_resident = p.w_resident != 0, skip_mma = (p.debug & 4) != 0;
+    const bool w_resident = p.w_resident != 0;
     const uint32_t idesc = umma_idesc_bf16(128, N);
     const uint64_t desc_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
     const uint32_t a_lo0 = (smem_u32(As) >> 4) | (static_cast<uint32_t>(p.R) << 16);  // LBO = R*16 B
     const uint32_t w_lo0 = (smem_u32(Ws) >> 4) | (static_cast<uint32_t>(N) << 16);    // LBO = N*16 B
     const uint32_t a_stage_u = p.a_stage_bytes >> 4, w_slab_u = p.w_slab_bytes >> 4;
+    const uint32_t a_half = X3 ? (a_stage_u >> 1) : 0u, w_half = X3 ? (w_slab_u >> 1) : 0u;  // hi image, then lo image
     const uint32_t kstep_a = 2 * p.R, kstep_w = 2 * N;
     const uint32_t acc_stride = p.n_tiles * N;
     if (w_resident && my_groups > 0) {
       if (leader) {  // the resident filter is fetched once per CTA
-        const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w) +
-                                  static_cast<size_t>(blockIdx.x % p.w_reps) * p.n_slabs * p.w_slab_bytes;
+        const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
         mbar_arrive_expect_tx(&bar_w_full[0], p.n_slabs * p.w_slab_bytes);
         for (int sidx = 0; sidx < p.n_slabs; ++sidx)
           bulk_g2s(Ws + sidx * p.w_slab_bytes, wg + static_cast<size_t>(sidx) * p.w_slab_bytes, p.w_slab_bytes, &bar_w_full[0]);
@@ -345,10 +396,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     }
     // The tap loop is unrolled at compile time (NTAPS = 9 or 1), the streamed and the resident filter get their own
     // copies of it, and nothing in it is looked up or divided: for N = 128 a tap is only eight MMAs (~540 cycles of
-    // tensor-core work), and the ~130 scalar instructions per tap of the generic loop (ring index arithmetic, tap
-    // rotation, debug / cluster branches, register->uniform moves) kept the single issuing thread BEHIND the tensor
-    // core -- 102 cycles per MMA issued against 67 executed (tools/probe_umma2.cu order 12).
-    const bool no_stream = (p.debug & 64) != 0;
+    // tensor-core work), and the ~130 scalar instructions per tap of a generic loop (ring index arithmetic, run-time
+    // branches, register->uniform moves) kept the single issuing thread BEHIND the tensor core -- 102 cycles per MMA
+    // issued against 67 executed (tools/probe_umma2.cu order 12).
     auto run = [&](auto nt_c, auto outer_c, auto taps_c) {
       constexpr int NT = decltype(nt_c)::value;
       constexpr bool TILE_OUTER = decltype(outer_c)::value;
@@ -362,35 +412,32 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       const uint32_t uN = static_cast<uint32_t>(N), uWp = static_cast<uint32_t>(Wp);
       for (int li = 0; li < my_groups; ++li) {
         const int buf = li % acc_bufs, useb = li / acc_bufs;
-        if (leader) RD_TRACE(0, li, 0);
         if (useb > 0) { mbar_wait(&bar_acc_empty[buf], (useb - 1) & 1); tc_fence_after_sync(); }
-        if (leader) RD_TRACE(0, li, 1);
         const uint32_t acc = tmem + buf * acc_stride;
         for (int chunk = 0; chunk < nchunks; ++chunk) {
           const int stage = a_stage_i;
           mbar_wait_addr(afull0 + 8 * stage, a_par);
           tc_fence_after_sync();
-          if (chunk == 0 && leader) RD_TRACE(0, li, 2);
           const uint32_t a_lo_stage = a_lo0 + stage * a_stage_u;
           if (w_resident) {
             const uint32_t w_chunk = w_lo0 + chunk * NTAPS * w_slab_u;
 #pragma unroll
             for (int t = 0; t < NTAPS; ++t) {
               const uint32_t shift = NTAPS == 9 ? (t / 3) * uWp + (t % 3) : 0u;  // tap (dy,dx) -> row shift dy*Wp + dx
-              if (leader && !skip_mma)
-                issue_tap<NT, TILE_OUTER>(acc, uN, a_lo_stage + shift, w_chunk + t * w_slab_u, kstep_a, kstep_w, desc_hi, idesc,
-                                          (chunk | t) != 0);
+              if (leader)
+                issue_tap<NT, TILE_OUTER, X3>(acc, uN, a_lo_stage + shift, w_chunk + t * w_slab_u, kstep_a, kstep_w, desc_hi,
+                                              idesc, (chunk | t) != 0, a_half, w_half);
             }
           } else {
 #pragma unroll
             for (int t = 0; t < NTAPS; ++t) {
               const uint32_t shift = NTAPS == 9 ? (t / 3) * uWp + (t % 3) : 0u;
-              if (!no_stream) { mbar_wait_addr(wfull0 + 8 * ws, w_par); tc_fence_after_sync(); }
+              mbar_wait_addr(wfull0 + 8 * ws, w_par);
+              tc_fence_after_sync();
               if (leader) {
-                if (!skip_mma)
-                  issue_tap<NT, TILE_OUTER>(acc, uN, a_lo_stage + shift, w_lo0 + ws * w_slab_u, kstep_a, kstep_w, desc_hi, idesc,
-                                            (chunk | t) != 0);
-                if (!no_stream) umma_commit_addr(wempty0 + 8 * ws);
+                issue_tap<NT, TILE_OUTER, X3>(acc, uN, a_lo_stage + shift, w_lo0 + ws * w_slab_u, kstep_a, kstep_w, desc_hi,
+                                              idesc, (chunk | t) != 0, a_half, w_half);
+                umma_commit_addr(wempty0 + 8 * ws);
               }
               if (++ws == w_stages) { ws = 0; w_par ^= 1; }
             }
@@ -398,10 +445,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           if (leader) umma_commit_addr(aempty0 + 8 * stage);  // operand stage reusable once these MMAs have read it
           if (++a_stage_i == a_stages) { a_stage_i = 0; a_par ^= 1; }
         }
-        if (leader) {
-          umma_commit(&bar_acc_full[buf]);
-          RD_TRACE(0, li, 3);
-        }
+        if (leader) umma_commit(&bar_acc_full[buf]);
       }
     };
     using std::integral_constant;
@@ -423,29 +467,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     __syncwarp();
   } else if (warp == 1) {
     // ================================================================ weight producer (streamed filters only)
-    if (lane == 0 && my_groups > 0 && !p.w_resident && !(p.debug & 64)) {  // debug bit 6: no filter stream at all (timing experiments)
-      const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w) +
-                                static_cast<size_t>((blockIdx.x / p.cluster) % p.w_reps) * p.n_slabs * p.w_slab_bytes;
+    if (lane == 0 && my_groups > 0 && !p.w_resident) {
+      const unsigned char* wg = reinterpret_cast<const unsigned char*>(p.w);
       const int total = my_groups * p.n_slabs;
-      const int tap0 = 0;  // natural tap order (a per-CTA rotation against L2 hot spots was measured to change nothing)
-      const int w_stages = p.w_stages, ntaps = p.ntaps, nchunks = p.nchunks;
-      // (slot, parity) and (chunk, tap) are counters, not `%` / `/` of the iteration index: this single thread has to
-      // turn a slab around in well under the ~500 cycles the tensor core needs to consume one
-      int ws = 0, e_par = 1, chunk = 0, k = 0, tap = tap0;
+      const int w_stages = p.w_stages, n_slabs = p.n_slabs;
+      // (slot, parity) and the slab index are counters, not `%` / `/` of the iteration index: this single thread has
+      // to turn a slab around in well under the ~500 cycles the tensor core needs to consume one
+      int ws = 0, e_par = 1, slab = 0;
       for (int it = 0; it < total; ++it) {
         if (it >= w_stages) mbar_wait(&bar_w_empty[ws], e_par);
         mbar_arrive_expect_tx(&bar_w_full[ws], p.w_slab_bytes);
-        const unsigned char* src = wg + static_cast<size_t>(chunk * ntaps + tap) * p.w_slab_bytes;
-        if (p.cluster > 1) {
-          // every CTA of the cluster fetches 1/cluster of the slab and multicasts it to all of them
-          const uint32_t part = p.w_slab_bytes / p.cluster;
-          bulk_g2s_multicast(Ws + ws * p.w_slab_bytes + crank * part, src + crank * part, part, &bar_w_full[ws], cmask);
-        } else {
-          bulk_g2s(Ws + ws * p.w_slab_bytes, src, p.w_slab_bytes, &bar_w_full[ws]);
-        }
+        bulk_g2s(Ws + ws * p.w_slab_bytes, wg + static_cast<size_t>(slab) * p.w_slab_bytes, p.w_slab_bytes, &bar_w_full[ws]);
         if (++ws == w_stages) { ws = 0; e_par ^= 1; }   // first wait on a slot (round 1) uses parity 0
-        if (++tap == ntaps) tap = 0;                      // this CTA's rotated tap order
-        if (++k == ntaps) { k = 0; tap = tap0; if (++chunk == nchunks) chunk = 0; }
+        if (++slab == n_slabs) slab = 0;                  // natural (chunk, tap) order, restarted for every group
       }
     }
     __syncwarp();
@@ -455,8 +489,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     const int et = q * 32 + lane;
     const int N = p.N, n_tiles = p.n_tiles, S = p.S;
     const float oscale = p.out_scale;
-    const bool skip_ld = (p.debug & 16) != 0, skip_work = (p.debug & 2) != 0;
-    const size_t out_gstride = static_cast<size_t>(S) * p.Ho * p.Wo * N;
+    const size_t out_gstride = static_cast<size_t>(S) * p.Ho * p.Wo * p.out_stride;
     // (bias + Dense_0(SiLU(temb))) * out_scale for every (sample, channel) of group g, written straight into one
     // half of the double-buffered table in shared memory (the other half is being read by the current group).
     auto bt_fill = [&](float* dst, int g) {
@@ -474,40 +507,43 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     };
     pdl_wait();  // tproj / residual come from earlier launches
     if (my_groups > 0) bt_fill(s_bt, blockIdx.x);
+    act_t* const outp = static_cast<act_t*>(p.out);
+    const act_t* const resp = static_cast<const act_t*>(p.residual);
     for (int li = 0; li < my_groups; ++li) {
       const int g = blockIdx.x + li * gridDim.x;
       const int S_act = max(0, min(S, p.B2 - g * S));
       const int buf = li % p.acc_bufs;
       const float* bt = s_bt + (li & 1) * S * N;
-      if (et == 0) RD_TRACE(1, li, 0);
       epi_bar();  // this group's table is complete; the other half is no longer read by anyone
-      if (et == 0) RD_TRACE(1, li, 1);
       // next group's table: its global-load latency hides behind the accumulator wait below.  (Requesting it into
       // registers before the rows and storing it after them was measured slower: +1.5 % conv time from the extra
       // register pressure in this 128-register role.)
       if (li + 1 < my_groups) bt_fill(s_bt + ((li + 1) & 1) * S * N, g + gridDim.x);
       mbar_wait(&bar_acc_full[buf], (li / p.acc_bufs) & 1);
       tc_fence_after_sync();
-      if (et == 0) RD_TRACE(1, li, 2);
       const uint32_t acc = tmem + buf * n_tiles * N + (static_cast<uint32_t>(q * 32) << 16);
-      __nv_bfloat16* og = p.out + static_cast<size_t>(g) * out_gstride;
-      const __nv_bfloat16* rg = p.residual ? p.residual + static_cast<size_t>(g) * out_gstride : nullptr;
-      const int valid_limit = S_act * p.Ho * p.Wo * N;
+      act_t* og = outp + static_cast<size_t>(g) * out_gstride;
+      const act_t* rg = resp ? resp + static_cast<size_t>(g) * out_gstride : nullptr;
+      const int valid_limit = S_act * p.Ho * p.Wo * p.out_stride;
       // A thread owns one accumulator row per 128-row tile and walks it in blocks of 32 columns.  One warp per TMEM
       // lane quarter runs this loop, so it is bound by dependent-instruction latency: per-row state is computed once
       // per tile, nothing is divided, and the residual of the next block is requested before the current one is used.
       for (int tile = 0; tile < n_tiles; ++tile) {
         const int row = tile * 128 + et;
         const int orow = t_orow[row];
-        const bool valid = orow >= 0 && orow < valid_limit && !skip_work;
+        const bool valid = orow >= 0 && orow < valid_limit;
         const float* btr = bt + t_os[row] * N;
-        if (rg) epi_row<true>(acc + tile * N, N, btr, oscale, rg + orow, og + orow, valid, skip_ld);
-        else epi_row<false>(acc + tile * N, N, btr, oscale, nullptr, og + orow, valid, skip_ld);
+        if constexpr (X3) {
+          if (rg) epi_row_f32<true>(acc + tile * N, N, btr, oscale, rg + orow, og + orow, valid);
+          else epi_row_f32<false>(acc + tile * N, N, btr, oscale, nullptr, og + orow, valid);
+        } else {
+          if (rg) epi_row<true>(acc + tile * N, N, btr, oscale, rg + orow, og + orow, valid);
+          else epi_row<false>(acc + tile * N, N, btr, oscale, nullptr, og + orow, valid);
+        }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
-      if (et == 0) RD_TRACE(1, li, 3);
     }
   } else {
     // ================================================================ transform (warps 2,3,8..15)
@@ -528,6 +564,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     }
     xform_bar();
     pdl_wait();  // the activations read below come from earlier launches
+    const act_t* const src0 = static_cast<const act_t*>(p.src[0]);
+    const act_t* const src1 = static_cast<const act_t*>(p.src[1]);
     const size_t gstride0 = static_cast<size_t>(p.S) * p.Hs[0] * p.Ws[0] * p.C[0];
     const size_t gstride1 = static_cast<size_t>(p.S) * p.Hs[1] * p.Ws[1] * p.C[1];
     const float inv_n = GNM != GNM_NONE ? 1.0f / static_cast<float>(p.cpg * P) : 0.0f;
@@ -565,15 +603,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       }
     };
     // (ca, cb) are pre-halved by gn_coeffs when SiLU follows: h = y/2, SiLU(y) = h + h*tanh(h)
-    auto gn_apply = [&](uint4& raw, const float (&ca)[8], const float (&cb)[8]) {
-      float f[8];
-      unpack8(raw, f);
+    auto gn_apply_f = [&](float (&f)[8], const float (&ca)[8], const float (&cb)[8]) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], ca[j], cb[j]);
       if (p.silu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], tanh_approx(f[j]), f[j]);
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], X3 ? tanhf(f[j]) : tanh_approx(f[j]), f[j]);
       }
+    };
+    auto gn_apply = [&](uint4& raw, const float (&ca)[8], const float (&cb)[8]) {
+      float f[8];
+      unpack8(raw, f);
+      gn_apply_f(f, ca, cb);
       raw = pack8(f);
     };
     // fixed-order two-step reduction of the per-thread partial records into per-(sample, group) mean / rstd:
@@ -610,7 +651,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       dst[3] = make_float4(sq[4], sq[5], sq[6], sq[7]);
     };
 
-    if (RC > 0) {
+    if constexpr (RC > 0) {
       // ---------------- register-cached mode: every thread owns one (sample, 8-channel chunk, pixel slice);
       // its pixels are read from global memory ONCE, kept in registers across the statistics barrier,
       // then normalised and written to the operand ring.  With RC == 8 the next group's pixels are
@@ -629,8 +670,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       uint4 raw[RCN], nxt[PREFETCH ? RCN : 1];
       auto load_group = [&](uint4* dst, int li) {
         const int g = blockIdx.x + li * gridDim.x;
-        const bool active = owner && s < min(p.S, p.B2 - g * p.S) && !(p.debug & 1);
-        const __nv_bfloat16* gbase = p.src[which] + static_cast<size_t>(g) * (which ? gstride1 : gstride0) + coff;
+        const bool active = owner && s < min(p.S, p.B2 - g * p.S);
+        const __nv_bfloat16* gbase = reinterpret_cast<const __nv_bfloat16*>(which ? src1 : src0) +
+                                     static_cast<size_t>(g) * (which ? gstride1 : gstride0) + coff;
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
           const int px = slice + k * PS;
@@ -641,8 +683,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
         const int S_act = max(0, min(p.S, p.B2 - g * p.S));
-        const bool active = owner && s < S_act && !(p.debug & 1);
-        if (xt == 0) RD_TRACE(2, li, 0);
+        const bool active = owner && s < S_act;
         if (!PREFETCH && li > 0) load_group(raw, li);
         float sum[8], sq[8];
 #pragma unroll
@@ -656,22 +697,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
           }
         }
-        if (!(p.debug & 32)) {
         if (owner) put_record(slice * pairs + pair, sum, sq);
-        if (xt == 0) RD_TRACE(2, li, 1);
         xform_bar();
-        if (xt == 0) RD_TRACE(2, li, 2);
         stat_reduce(0, S_act, pairs, PS);
         xform_bar();
-        }
-        if (xt == 0) RD_TRACE(2, li, 3);
         if (PREFETCH && li + 1 < my_groups) load_group(nxt, li + 1);
         float ca[8], cb[8];
         if (active) gn_coeffs(s, kc * 8, ca, cb);
         for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
           const int stage = a_it % p.a_stages;
           if (a_it >= p.a_stages) mbar_wait_relaxed(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
-          if (xt == 0 && chunk == 0) RD_TRACE(2, li, 4);
           if (active && chunk == my_chunk) {
             uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes) + kcl * p.R;
 #pragma unroll
@@ -683,19 +718,16 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               }
             }
           }
-          if (xt == 0 && chunk == 0) RD_TRACE(2, li, 5);
-          if (!(p.debug & 8)) fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
-          if (xt == 0 && chunk == 0) RD_TRACE(2, li, 6);
+          fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
           xform_bar();
           if (xt == 0) mbar_arrive(&bar_a_full[stage]);
-          if (xt == 0 && chunk == 0) RD_TRACE(2, li, 7);
         }
         if (PREFETCH) {
 #pragma unroll
           for (int k = 0; k < RC; ++k) raw[k] = nxt[k];
         }
       }
-    } else if (GNM == GNM_NONE) {
+    } else if constexpr (GNM == GNM_NONE && !X3) {
       // ---------------- plain gather (NIN shortcuts, up/down-sampling convs, attention projections): there is nothing
       // to compute, so the pixels go global -> shared with 16-byte cp.async copies straight into their K-major slots,
       // one whole 64-channel chunk ahead of the chunk being handed to the tensor core (no registers, ~64 KB in
@@ -707,17 +739,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const int S_act = max(0, min(p.S, p.B2 - g * p.S));
         const int stage = it % p.a_stages;
         if (it >= p.a_stages) mbar_wait_relaxed(&bar_a_empty[stage], ((it / p.a_stages) - 1) & 1);
-        if (!(p.debug & 1)) {
-          uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes);
-          const int which = (chunk * 64 < p.C[0]) ? 0 : 1;
-          const __nv_bfloat16* base = (which ? p.src[1] + static_cast<size_t>(g) * gstride1 - p.C[0]
-                                             : p.src[0] + static_cast<size_t>(g) * gstride0) + chunk * 64;
-          const int* toff = t_off + (which ? p.S * P : 0);
-          const int items = S_act * P * 8;
-          for (int item = xt; item < items; item += XFORM_THREADS) {
-            const int sp = item >> 3, kcl = item & 7;
-            cp_async16(a4 + kcl * p.R + t_row[sp], base + toff[sp] + kcl * 8);
-          }
+        uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes);
+        const int which = (chunk * 64 < p.C[0]) ? 0 : 1;
+        const act_t* base = (which ? src1 + static_cast<size_t>(g) * gstride1 - p.C[0]
+                                   : src0 + static_cast<size_t>(g) * gstride0) + chunk * 64;
+        const int* toff = t_off + (which ? p.S * P : 0);
+        const int items = S_act * P * 8;
+        for (int item = xt; item < items; item += XFORM_THREADS) {
+          const int sp = item >> 3, kcl = item & 7;
+          cp_async16(a4 + kcl * p.R + t_row[sp], base + toff[sp] + kcl * 8);
         }
         cp_async_commit();
       };
@@ -729,12 +759,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         if (xt == 0) mbar_arrive(&bar_a_full[it % p.a_stages]);
       }
     } else {
-      // ---------------- streaming mode: statistics pass, then a normalise pass per chunk
+      // ---------------- streaming mode: statistics pass, then a normalise pass per chunk (also the only transform of
+      // the fp32-class mode, where a pixel's 8 channels are 32 bytes of fp32 and leave as a bf16 hi and a bf16 lo vector)
+      const int a_half16 = p.a_stage_bytes / 32;  // uint4 index of the lo image inside a stage (x3)
+      auto load8 = [&](const act_t* ptr, uint4& raw, float (&f)[8]) {
+        if constexpr (X3) ldg8f(reinterpret_cast<const float*>(ptr), f);
+        else raw = __ldg(reinterpret_cast<const uint4*>(ptr));
+      };
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
         const int S_act = max(0, min(p.S, p.B2 - g * p.S));
-        const __nv_bfloat16* gb0 = p.src[0] + static_cast<size_t>(g) * gstride0;
-        const __nv_bfloat16* gb1 = p.nsrc > 1 ? p.src[1] + static_cast<size_t>(g) * gstride1 : gb0;
+        const act_t* gb0 = src0 + static_cast<size_t>(g) * gstride0;
+        const act_t* gb1 = p.nsrc > 1 ? src1 + static_cast<size_t>(g) * gstride1 : gb0;
         if (GNM != GNM_NONE) {
           // deterministic statistics: per-thread partial records reduced in a fixed order, in batches of samples
           const int spb = max(1, STAT_PAIRS / p.KC);
@@ -747,24 +783,30 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               const int pair = item % pairs, slice = item / pairs;
               const int s = pair / p.KC, kc = pair - s * p.KC;
               const int which = (kc * 8 < p.C[0]) ? 0 : 1;
-              const __nv_bfloat16* base = (which ? gb1 - p.C[0] : gb0) + kc * 8;
+              const act_t* base = (which ? gb1 - p.C[0] : gb0) + kc * 8;
               const int* toff = t_off + (which ? p.S * P : 0) + (sb + s) * P;
               float sum[8], sq[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; sq[j] = 0.0f; }
-              constexpr int SB = 4;  // (12 in flight was measured slower: the streaming variants spill at the 128-register cap)
+              constexpr int SB = X3 ? 2 : 4;  // (12 in flight was measured slower: the streaming variants spill at the 128-register cap)
               for (int px = slice; px < P; px += SB * PS) {
                 uint4 raw[SB];
+                float f[X3 ? SB : 1][8];
 #pragma unroll
                 for (int u = 0; u < SB; ++u)
-                  if (px + u * PS < P) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + toff[px + u * PS]));
+                  if (px + u * PS < P) load8(base + toff[px + u * PS], raw[u], f[X3 ? u : 0]);
 #pragma unroll
                 for (int u = 0; u < SB; ++u)
                   if (px + u * PS < P) {
-                    float f[8];
-                    unpack8(raw[u], f);
+                    float ff[8];
+                    if constexpr (X3) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
+                      for (int j = 0; j < 8; ++j) ff[j] = f[u][j];
+                    } else {
+                      unpack8(raw[u], ff);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { sum[j] += ff[j]; sq[j] = fmaf(ff[j], ff[j], sq[j]); }
                   }
               }
               put_record(slice * pairs + pair, sum, sq);
@@ -780,27 +822,34 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           if (a_it >= p.a_stages) mbar_wait_relaxed(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
           uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes);
           const int which = (chunk * 64 < p.C[0]) ? 0 : 1;  // C[0] is a multiple of 64 whenever there are two sources
-          const __nv_bfloat16* base = (which ? gb1 - p.C[0] : gb0) + chunk * 64;
+          const act_t* base = (which ? gb1 - p.C[0] : gb0) + chunk * 64;
           const int* toff = t_off + (which ? p.S * P : 0);
-          constexpr int NB = 8;
+          constexpr int NB = X3 ? 4 : 8;
           for (int b0 = xt; b0 < items; b0 += NB * XFORM_THREADS) {
             uint4 raw[NB];
+            float f[X3 ? NB : 1][8];
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
               const int item = b0 + u * XFORM_THREADS;
-              if (item < items) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + toff[item >> 3] + (item & 7) * 8));
+              if (item < items) load8(base + toff[item >> 3] + (item & 7) * 8, raw[u], f[X3 ? u : 0]);
             }
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
               const int item = b0 + u * XFORM_THREADS;
               if (item < items) {
                 const int sp = item >> 3, kcl = item & 7;
-                if (GNM != GNM_NONE) {
-                  float ca[8], cb[8];
-                  gn_coeffs(sp / P, chunk * 64 + kcl * 8, ca, cb);
-                  gn_apply(raw[u], ca, cb);
+                float ca[8], cb[8];
+                if (GNM != GNM_NONE) gn_coeffs(sp / P, chunk * 64 + kcl * 8, ca, cb);
+                if constexpr (X3) {
+                  if (GNM != GNM_NONE) gn_apply_f(f[u], ca, cb);
+                  uint4 hi, lo;
+                  split8(f[u], hi, lo);
+                  a4[kcl * p.R + t_row[sp]] = hi;
+                  a4[a_half16 + kcl * p.R + t_row[sp]] = lo;
+                } else {
+                  if (GNM != GNM_NONE) gn_apply(raw[u], ca, cb);
+                  a4[kcl * p.R + t_row[sp]] = raw[u];
                 }
-                a4[kcl * p.R + t_row[sp]] = raw[u];
               }
             }
           }
@@ -814,7 +863,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 
   tc_fence_before_sync();
   __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers
   if (warp == 0) tmem_dealloc(tmem, p.tmem_cols);
 }
 
@@ -834,33 +882,46 @@ static int next_pow2_cols(int c) {
   return v;
 }
 
-static int conv_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = kNumSMs;
-  }
-  return sms;
+constexpr int MAX_DEVICES = 64;
+
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+  return dev;
 }
 
-static long long* g_trace = nullptr;
-static int g_trace_groups = 0;
+// SM count of the CURRENT device (one process may drive several GPUs; launch state is kept per device ordinal)
+static int conv_num_sms() {
+  static int sms[MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0) sms[dev] = kNumSMs;
+  }
+  return sms[dev];
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 // Fills the launch geometry for an op; returns RD_OK or an error.
 int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& grid) {
   RD_REQUIRE(op.nsrc == 1 || op.nsrc == 2, "conv: nsrc must be 1 or 2");
   RD_REQUIRE(op.ntaps == 9 || op.ntaps == 1, "conv: ntaps must be 9 or 1");
   RD_REQUIRE(op.H_in >= 1 && op.W_in >= 1 && op.H_in <= MAX_HW && op.W_in <= MAX_HW, "conv: H,W must be in [1,%d]", MAX_HW);
-  RD_REQUIRE(op.C_out % 32 == 0 && op.C_out >= 32 && op.C_out <= 256, "conv: C_out %d unsupported", op.C_out);
+  RD_REQUIRE(op.C_out % 32 == 0 && op.C_out >= 32 && op.C_out <= 256, "conv: C_out %d unsupported per launch (slice it, see out_stride)", op.C_out);
+  RD_REQUIRE(op.out_stride == 0 || (op.out_stride >= op.C_out && op.out_stride % 8 == 0), "conv: out_stride %d < C_out %d", op.out_stride, op.C_out);
   RD_REQUIRE(op.stride == 1 || (op.stride == 2 && op.pad == 0 && op.ntaps == 9), "conv: stride 2 needs pad 0, 3x3");
   RD_REQUIRE(op.w && op.bias && op.out && op.B2 > 0, "conv: null pointer / empty batch");
+  RD_REQUIRE(op.precision == RD_PREC_BF16 || op.precision == RD_PREC_F32X3, "conv: unknown precision %d", op.precision);
   memset(&p, 0, sizeof(p));
+  p.x3 = op.precision == RD_PREC_F32X3;
   int cin = 0;
   for (int i = 0; i < op.nsrc; ++i) {
     RD_REQUIRE(op.src[i].ptr && op.src[i].C % 8 == 0 && op.src[i].C > 0, "conv: source %d channels must be a multiple of 8", i);
     RD_REQUIRE(op.src[i].Hs >= 1 && op.src[i].Ws >= 1 && op.src[i].Hs <= MAX_HW && op.src[i].Ws <= MAX_HW, "conv: bad source size");
-    p.src[i] = static_cast<const __nv_bfloat16*>(op.src[i].ptr);
+    p.src[i] = op.src[i].ptr;
     p.C[i] = op.src[i].C; p.Hs[i] = op.src[i].Hs; p.Ws[i] = op.src[i].Ws;
     nearest_map(p.ymap[i], op.H_in, op.src[i].Hs);
     nearest_map(p.xmap[i], op.W_in, op.src[i].Ws);
@@ -882,6 +943,7 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   if (op.stride == 1) RD_REQUIRE(op.H_out == op.H_in && op.W_out == op.W_in, "conv: stride-1 output must match input size");
   else RD_REQUIRE(op.H_out == (op.H_in + 1 - 3) / 2 + 1 && op.W_out == (op.W_in + 1 - 3) / 2 + 1, "conv: bad downsample output size");
   p.Cin = cin; p.KC = cin / 8; p.nchunks = cin / 64; p.N = op.C_out;
+  p.out_stride = op.out_stride ? op.out_stride : op.C_out;
   p.groups = op.gn_groups; p.silu = op.gn_silu; p.eps = op.gn_eps;
   p.gnm = GNM_NONE;
   if (p.groups > 0) {
@@ -892,15 +954,10 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   p.gamma = op.gn_gamma; p.beta = op.gn_beta;
   p.w = static_cast<const __nv_bfloat16*>(op.w);
   p.bias = op.bias; p.tproj = op.tproj; p.tproj_stride = op.tproj_stride; p.tproj_off = op.tproj_off; p.tproj_wrap = op.tproj_wrap;
-  p.residual = static_cast<const __nv_bfloat16*>(op.residual);
-  p.out_scale = op.out_scale; p.out = static_cast<__nv_bfloat16*>(op.out); p.B2 = op.B2;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("RD_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
-    p.debug = dbg;
-    p.trace = g_trace; p.trace_groups = g_trace_groups;
-  }
-  p.w_slab_bytes = p.N * 128;
+  p.residual = op.residual;
+  p.out_scale = op.out_scale; p.out = op.out; p.B2 = op.B2;
+  const int planes = p.x3 ? 2 : 1;  // hi + lo images of every operand in the fp32-class mode
+  p.w_slab_bytes = p.N * 128 * planes;
   p.n_slabs = p.nchunks * p.ntaps;
 
   // Tile geometry.  Per candidate tile count: samples per group, row efficiency, whether the TMEM
@@ -912,54 +969,20 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   const int valid_px = op.H_out * op.W_out;
   double best_score = -1.0;
   ConvParams best = p;
-  static int wmax = -1, astream = 3;
-  static double single_pen = 0.75, tie_eps = 0.0;
-  static int res2 = 0;
-  if (wmax < 0) {
-    const char* e = getenv("RD_CONV_WSTAGES");
-    wmax = e ? atoi(e) : 4;
-    if (wmax < 2) wmax = 2;
-    if (wmax > MAX_W_STAGES) wmax = MAX_W_STAGES;
-    if ((e = getenv("RD_CONV_ASTAGES_STREAM"))) astream = atoi(e) <= 2 ? 2 : 3;
-    if ((e = getenv("RD_CONV_SINGLE_PEN"))) single_pen = atof(e);
-    if ((e = getenv("RD_CONV_RES2"))) res2 = atoi(e);
-    if ((e = getenv("RD_CONV_TIE_EPS"))) tie_eps = atof(e);  // streamed filters: a larger group wins when within tie_eps
-  }
-  // RD_CONV_FORCE_NT="cin,n,h,nt;..." pins the tile count of the layers with that (C_in, C_out, H_in) -- geometry experiments
-  int force_nt = 0, force_s = 0;
-  {
-    static const char* sspec = getenv("RD_CONV_FORCE_S");  // "cin,n,h,S;...": cap on the samples per group
-    for (const char* q = sspec; q && *q;) {
-      int a = 0, b = 0, c = 0, d = 0;
-      if (sscanf(q, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a == cin && b == p.N && c == op.H_in) force_s = d;
-      q = strchr(q, ';');
-      if (q) ++q;
-    }
-    static const char* spec = getenv("RD_CONV_FORCE_NT");
-    for (const char* q = spec; q && *q;) {
-      int a = 0, b = 0, c = 0, d = 0;
-      if (sscanf(q, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a == cin && b == p.N && c == op.H_in) force_nt = d;
-      q = strchr(q, ';');
-      if (q) ++q;
-    }
-  }
+  // measurement switches (read once; defaults are the shipped configuration)
+  static const int wmax = [] { int w = env_int("RD_CONV_WSTAGES", 4); return w < 2 ? 2 : (w > MAX_W_STAGES ? MAX_W_STAGES : w); }();
+  static const int astream = env_int("RD_CONV_ASTAGES_STREAM", 3) <= 2 ? 2 : 3;
   for (int nt = 1; nt <= 4; ++nt) {
     if (nt * p.N > 512 || nt * 128 < p.rps) continue;
-    if (force_nt && nt != force_nt) continue;
     ConvParams c = p;
     c.n_tiles = nt;
     c.R = (nt * 128 + max_shift) | 1;
     c.S = (nt * 128) / p.rps;
     if (op.samples_per_cta > 0 && op.samples_per_cta < c.S) c.S = op.samples_per_cta;
-    if (force_s > 0 && force_s < c.S) c.S = force_s;
     c.acc_bufs = (2 * nt * p.N <= 512) ? 2 : 1;
-    c.a_stage_bytes = (8 * c.R * 16 + 127) / 128 * 128;
+    c.a_stage_bytes = (8 * c.R * 16 + 127) / 128 * 128 * planes;
     c.a_stages = (p.nchunks == 1) ? 2 : 3;
     c.w_resident = 1;
-    if (res2 && conv_smem_layout(c).total > smem_cap && c.a_stages == 3) {
-      c.a_stages = 2;  // a resident filter is worth more than the third operand stage
-      if (conv_smem_layout(c).total > smem_cap) c.a_stages = 3;
-    }
     if (conv_smem_layout(c).total > smem_cap) {
       // Streamed filter: the ring has to cover the L2 latency of a slab at the rate the tensor core consumes them
       // (8-16 KB per ~600 cycles), i.e. tens of KB in flight -- it gets whatever shared memory two operand stages
@@ -970,49 +993,46 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
       if (c.w_stages < 2) c.w_stages = 2;
       while (c.w_stages > 2 && conv_smem_layout(c).total > smem_cap) --c.w_stages;
       if (conv_smem_layout(c).total > smem_cap && c.a_stages == 3) c.a_stages = 2;
+      if (conv_smem_layout(c).total > smem_cap) c.a_stages = 1;  // last resort (fp32-class plan at 16x16): transform and MMAs alternate
       if (conv_smem_layout(c).total > smem_cap) continue;
     }
-    // transform mode: register-cached when every (sample, chunk) pair gets a thread and <= 16 pixels
+    // transform mode: register-cached when every (sample, chunk) pair gets a thread and <= 16 pixels (bf16 only)
     c.xmode = 0; c.rc_PS = 1;
-    if (p.groups > 0 && c.S * p.KC <= XFORM_THREADS) {
+    if (!p.x3 && p.groups > 0 && c.S * p.KC <= XFORM_THREADS) {
       int ps = XFORM_THREADS / (c.S * p.KC);
       if (ps > p.H * p.W) ps = p.H * p.W;
       const int slots = (p.H * p.W + ps - 1) / ps;
       if (slots <= 16) { c.xmode = slots <= 8 ? 8 : 16; c.rc_PS = ps; }
     }
     double score = static_cast<double>(c.S * valid_px) / (nt * 128);
-    if (c.acc_bufs == 1) score *= (c.w_resident ? 0.75 : single_pen);
+    if (c.acc_bufs == 1) score *= 0.75;
     if (!c.w_resident) score *= (nt >= 2 ? 0.97 : 0.85);  // streamed weights are re-read per group: favour larger groups
-    if (score > best_score + (c.w_resident ? 0.0 : -tie_eps)) { best_score = score; best = c; }
+    if (score > best_score) { best_score = score; best = c; }
   }
-  RD_REQUIRE(best_score > 0, "conv: no tile geometry fits (Cin=%d N=%d rps=%d)", cin, p.N, p.rps);
+  RD_REQUIRE(best_score > 0, "conv: no tile geometry fits (Cin=%d N=%d rps=%d x3=%d)", cin, p.N, p.rps, p.x3);
   p = best;
   p.n_groups = (op.B2 + p.S - 1) / p.S;
-  p.n_issuers = 1;
-  p.cluster = 1;
-  {
-    static int reps = -1;
-    if (reps < 0) { const char* e = getenv("RD_CONV_WREPS"); reps = e ? atoi(e) : 1; if (reps < 1) reps = 1; if (reps > 16) reps = 16; }
-    p.w_reps = reps;  // rdb200/pack.py stores that many copies of every filter
-  }
-  // (thread-block clusters sharing the streamed filter by TMA multicast were built and measured in round 1: no gain for
-  //  2 CTAs, a loss for 4 -- the stream was never L2-bound, see DESIGN.md -- and the issue loop no longer carries the
-  //  multicast commit, so launches are always un-clustered)
   p.tmem_cols = next_pow2_cols(p.acc_bufs * p.n_tiles * p.N);
   smem_bytes = conv_smem_layout(p).total;
   const int sms = conv_num_sms();
   grid = p.n_groups < sms ? p.n_groups : sms;
-  if (p.cluster > 1) {
-    grid = grid / p.cluster * p.cluster;
-    if (grid == 0) { p.cluster = 1; grid = p.n_groups < sms ? p.n_groups : sms; }
-  }
   return RD_OK;
 }
 
 typedef void (*conv_kernel_t)(const ConvParams);
 
-static conv_kernel_t conv_pick(int gnm, int rc) {
-#define RD_K(G, R) conv_gemm_kernel<G, R>
+static conv_kernel_t conv_pick(int gnm, int rc, int x3) {
+#define RD_K(G, R) conv_gemm_kernel<G, R, false>
+#define RD_K3(G) conv_gemm_kernel<G, 0, true>
+  if (x3) {
+    switch (gnm) {
+      case GNM_NONE: return RD_K3(GNM_NONE);
+      case GNM_CPG8: return RD_K3(GNM_CPG8);
+      case GNM_CPG4: return RD_K3(GNM_CPG4);
+      case GNM_GENERAL: return RD_K3(GNM_GENERAL);
+      default: return nullptr;
+    }
+  }
   switch (gnm * 100 + rc) {
     case GNM_NONE * 100 + 0: return RD_K(GNM_NONE, 0);
     case GNM_CPG8 * 100 + 0: return RD_K(GNM_CPG8, 0);
@@ -1027,6 +1047,7 @@ static conv_kernel_t conv_pick(int gnm, int rc) {
     default: return nullptr;
   }
 #undef RD_K
+#undef RD_K3
 }
 
 int conv_launch(const rd_op_conv& op, cudaStream_t st) {
@@ -1034,52 +1055,29 @@ int conv_launch(const rd_op_conv& op, cudaStream_t st) {
   int smem = 0, grid = 0;
   int rc = conv_make_params(op, p, smem, grid);
   if (rc != RD_OK) return rc;
-  conv_kernel_t k = conv_pick(p.gnm, p.xmode);
-  if (!k) return fail(RD_E_STATE, "conv: no kernel for gnm=%d rc=%d", p.gnm, p.xmode);
-  static bool configured[4][17] = {};
-  if (!configured[p.gnm][p.xmode]) {
+  conv_kernel_t k = conv_pick(p.gnm, p.xmode, p.x3);
+  if (!k) return fail(RD_E_STATE, "conv: no kernel for gnm=%d rc=%d x3=%d", p.gnm, p.xmode, p.x3);
+  // cudaFuncSetAttribute is per (function, device): a process that drives several GPUs opts in on each of them
+  static bool configured[MAX_DEVICES][2][4][17] = {};
+  bool& done = configured[current_device()][p.x3][p.gnm][p.xmode];
+  if (!done) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured[p.gnm][p.xmode] = true;
+    done = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(CONV_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[3];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = p.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[1];
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  static int pdl = -1;
-  if (pdl < 0) { const char* ev = getenv("RD_CONV_PDL"); pdl = ev ? atoi(ev) : 1; }  // RD_CONV_PDL=0 restores fully serialised launches (A/B measurements)
+  cfg.numAttrs = 0;
+  static const int pdl = env_int("RD_CONV_PDL", 1);  // RD_CONV_PDL=0 restores fully serialised launches (A/B measurements)
   if (pdl) {
     attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
     ++cfg.numAttrs;
-  }
-  // Optional (RD_CONV_L2_PERSIST=1): mark streamed filters as persisting in L2.  Off by default: it never changed the
-  // sampler's throughput (the 12.5 MB of filters stay L2-resident anyway) and the 32 MB set-aside it needs took 25 %
-  // off the bandwidth of unrelated streaming kernels in the same process (cube.reflect: 87 % -> 65 % of HBM peak).
-  static int l2_persist = -1;
-  if (l2_persist < 0) {
-    const char* ev = getenv("RD_CONV_L2_PERSIST");
-    l2_persist = ev ? atoi(ev) : 0;
-    if (l2_persist) {
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 32u << 20) != cudaSuccess) { l2_persist = 0; (void)cudaGetLastError(); }
-    }
-  }
-  if (l2_persist && !p.w_resident) {
-    cudaLaunchAttribute& a = attr[cfg.numAttrs++];
-    a.id = cudaLaunchAttributeAccessPolicyWindow;
-    a.val.accessPolicyWindow.base_ptr = const_cast<void*>(static_cast<const void*>(p.w));
-    a.val.accessPolicyWindow.num_bytes = static_cast<size_t>(p.n_slabs) * p.w_slab_bytes * p.w_reps;
-    a.val.accessPolicyWindow.hitRatio = 1.0f;
-    a.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    a.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   }
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, p);
   if (e != cudaSuccess) return fail(static_cast<int>(e), "conv_gemm_kernel launch: %s", cudaGetErrorString(e));
@@ -1087,12 +1085,6 @@ int conv_launch(const rd_op_conv& op, cudaStream_t st) {
 }
 
 }  // namespace rd
-
-extern "C" int rd_conv_set_trace(long long* buf, int groups) {
-  rd::g_trace = buf;
-  rd::g_trace_groups = groups;
-  return RD_OK;
-}
 
 extern "C" int rd_conv_launch_info(const rd_op_conv* op, int* smem_bytes, int* grid, int* rows_alloc) {
   RD_REQUIRE(op, "rd_conv_launch_info: null op");

@@ -98,11 +98,41 @@ __global__ void __launch_bounds__(128) gto_halo_decode_kernel(const float* __res
   o[t + 2] = __fadd_rn(__fmul_rn(unnorm(in[t + 2]), c.manifold_length_span), c.manifold_length_min);
 }
 
+// dataset row -> latent (reference Reflected-Diffusion/datasets.py:82-98, GTOHaloImageDataset.__getitem__): the row's
+// n_in values are zero-padded to the latent size, then EVERY entry (padding included) is z-scored, fp32 like numpy's.
+__global__ void __launch_bounds__(256) gto_halo_encode_kernel(const float* __restrict__ raw, float* __restrict__ lat,
+                                                              float* __restrict__ label, size_t n, int n_in, int n_lat,
+                                                              float mean, float std) {
+  const size_t total = n * static_cast<size_t>(n_lat);
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < total; i += stride) {
+    const size_t s = i / n_lat;
+    const int j = static_cast<int>(i - s * n_lat);
+    const float v = j < n_in ? raw[s * n_in + j] : 0.0f;
+    lat[i] = __fdiv_rn(__fsub_rn(v, mean), std);
+    if (j == 0 && label) label[s] = v;  // class label = the un-normalised first value (datasets.py:92)
+  }
+}
+
 }  // namespace rd
 
 using namespace rd;
 
 extern "C" {
+
+int rd_gto_halo_encode_f32(const float* raw, float* latents, float* labels, size_t n, size_t n_in, size_t n_latent,
+                           float data_mean, float data_std, void* stream) {
+  if (n == 0) return RD_OK;
+  RD_REQUIRE(raw && latents, "rd_gto_halo_encode_f32: null pointer");
+  RD_REQUIRE(n_in >= 1 && n_in <= n_latent && n_latent <= (1u << 20), "rd_gto_halo_encode_f32: %zu values do not fit a latent of %zu",
+             n_in, n_latent);
+  size_t blocks = (n * n_latent + 255) / 256;
+  if (blocks > static_cast<size_t>(kNumSMs) * 16) blocks = static_cast<size_t>(kNumSMs) * 16;
+  gto_halo_encode_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      raw, latents, labels, n, static_cast<int>(n_in), static_cast<int>(n_latent), data_mean, data_std);
+  return check_launch("gto_halo_encode_kernel");
+}
 
 int rd_perturb_reflect_f32(const float* x0, const float* z, const float* std, float* out, size_t B, size_t D,
                            void* stream) {

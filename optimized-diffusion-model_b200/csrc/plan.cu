@@ -39,35 +39,41 @@ static int run_op(const rd_op& op, cudaStream_t st) {
   }
 }
 
-// one predictor-corrector iteration: [corrector: score, norms, apply] x n, then [score, predictor]
+// one predictor-corrector iteration: [corrector: score, norms, apply] x n_corrector_steps, then [score, predictor]
+// (sampling.py:327-332 with ReflectedLangevinCorrector.update_fn :221-231 looping n_steps times).
+// Noise: tape slots per iteration are [corrector 0 .. n-1, predictor]; in Philox mode corrector move c draws from
+// stream (c * kDrawStride + 2*step), the predictor from (2*step + 1) -- disjoint for any grid below kDrawStride/2 points.
+constexpr uint32_t kDrawStride = 1u << 22;
+
 static int enqueue_iteration(rd_sampler* s, cudaStream_t st, int* launches) {
   const rd_sampler_desc& d = s->d;
   const size_t n = static_cast<size_t>(d.B) * d.D;
-  const int draws_per_step = d.n_corrector_steps > 0 ? 2 : 1;
+  const size_t draws_per_step = static_cast<size_t>(d.n_corrector_steps) + 1;
+  // The time-embedding projections depend on (step, labels) only, not on x: the first forward of an iteration fills
+  // them, every later forward of the same iteration skips the temb launch (the step counter advances after the predictor).
+  const int has_temb = (rd_plan_size(d.forward) > 1 && d.forward->ops[0].kind == RD_OP_TEMB) ? 1 : 0;
   int count = 0;
   int rc;
-  for (int c = 0; c < d.n_corrector_steps; ++c) {
-    if ((rc = rd_plan_run(d.forward, st)) != RD_OK) return rc;
-    count += rd_plan_size(d.forward);
-    int nblk = 0;
-    const float* noise = d.noise_tape;  // tape slot 2*step + 0
-    if ((rc = rd_pc_norms(d.score, noise, d.partial, &nblk, d.B, d.D, d.seed, 0, d.step_ctr, 2 * n, st)) != RD_OK) return rc;
-    if ((rc = rd_pc_corrector_apply(d.x, d.score, noise, d.partial, nblk, d.snr, d.x, nullptr, nullptr, d.B, d.D, d.seed, 0,
-                                    d.step_ctr, 2 * n, st)) != RD_OK)
-      return rc;
-    count += 2;
+  for (int c = 0; c <= d.n_corrector_steps; ++c) {
+    const int skip = c > 0 ? has_temb : 0;
+    if ((rc = rd_plan_run_range(d.forward, skip, rd_plan_size(d.forward) - skip, st)) != RD_OK) return rc;
+    count += rd_plan_size(d.forward) - skip;
+    const float* noise = d.noise_tape ? d.noise_tape + static_cast<size_t>(c) * n : nullptr;
+    if (c < d.n_corrector_steps) {
+      int nblk = 0;
+      const uint32_t base = static_cast<uint32_t>(c) * kDrawStride;
+      if ((rc = rd_pc_norms(d.score, noise, d.partial, &nblk, d.B, d.D, d.seed, base, d.step_ctr, draws_per_step * n, st)) != RD_OK) return rc;
+      if ((rc = rd_pc_corrector_apply(d.x, d.score, noise, d.partial, nblk, d.snr, d.x, nullptr, nullptr, d.B, d.D, d.seed, base,
+                                      d.step_ctr, draws_per_step * n, st)) != RD_OK)
+        return rc;
+      count += 2;
+    } else {
+      if ((rc = rd_pc_predictor_step(d.x, d.score, noise, d.g_table, d.dt, d.sqrt_dt, d.x, nullptr, d.B, d.D, d.seed, 0, d.step_ctr,
+                                     draws_per_step * n, 1, 0, st)) != RD_OK)
+        return rc;
+      count += 2;  // the update + the step-counter advance it carries
+    }
   }
-  // The time-embedding projections depend on (step, labels) only, not on x: when a corrector forward of this
-  // iteration has already filled them, the predictor forward skips the temb launch (the step counter advances after
-  // the predictor).
-  const int skip = (d.n_corrector_steps > 0 && rd_plan_size(d.forward) > 1 && d.forward->ops[0].kind == RD_OP_TEMB) ? 1 : 0;
-  if ((rc = rd_plan_run_range(d.forward, skip, rd_plan_size(d.forward) - skip, st)) != RD_OK) return rc;
-  count += rd_plan_size(d.forward) - skip;
-  const float* z = d.noise_tape ? d.noise_tape + (draws_per_step - 1) * n : nullptr;
-  if ((rc = rd_pc_predictor_step(d.x, d.score, z, d.g_table, d.dt, d.sqrt_dt, d.x, nullptr, d.B, d.D, d.seed, 0, d.step_ctr,
-                                 draws_per_step * n, 1, 0, st)) != RD_OK)
-    return rc;
-  count += 2;
   if (launches) *launches = count;
   return RD_OK;
 }
@@ -115,7 +121,7 @@ int rd_sampler_create(const rd_sampler_desc* d, rd_sampler** out) {
   RD_REQUIRE(s, "rd_sampler_create: out of memory");
   s->d = *d;
   s->launches_per_iter = (d->n_corrector_steps + 1) * rd_plan_size(d->forward) + 2 * d->n_corrector_steps + 2;
-  if (d->n_corrector_steps > 0 && rd_plan_size(d->forward) > 1 && d->forward->ops[0].kind == RD_OP_TEMB) s->launches_per_iter -= 1;
+  if (rd_plan_size(d->forward) > 1 && d->forward->ops[0].kind == RD_OP_TEMB) s->launches_per_iter -= d->n_corrector_steps;
   *out = s;
   return RD_OK;
 }

@@ -8,6 +8,7 @@
 #include "rd_common.h"
 #include <cuda_bf16.h>
 #include "rd_ptx.cuh"
+#include <type_traits>
 
 namespace rd {
 
@@ -146,8 +147,9 @@ int temb_launch(const rd_op_temb& op, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // input_conv: one thread per (sample, pixel) computes all C_out channels (weights broadcast from shared memory),
 // writes its 2*C_out bytes with 256-bit stores; NHWC bf16 out.  C_out <= 64 per pass (template-free: register tile of 64).
+template <typename TO>
 __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B,
+                                                      const float* __restrict__ bias, TO* __restrict__ out, int B,
                                                       int B2, int Cin, int Cout, int H, int W) {
   extern __shared__ __align__(16) float sw[];  // [Cin*9][Cout] (tap-major) + bias[Cout]
   // the conv launch that follows may start its prologue as SMs free up (it waits for this grid before reading `out`)
@@ -192,16 +194,26 @@ __global__ void __launch_bounds__(256) in_conv_kernel(const float* __restrict__ 
             }
           }
         }
-      __nv_bfloat16* dst = out + static_cast<size_t>(pix) * Cout + c0;
+      TO* dst = out + static_cast<size_t>(pix) * Cout + c0;
+      if constexpr (std::is_same<TO, float>::value) {
 #pragma unroll
-      for (int j16 = 0; j16 < 4; ++j16) {   // whole 32-byte sectors per store
-        u32x8 pk;
+        for (int j8 = 0; j8 < 8; ++j8) {
+          u32x8 pk;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(acc[16 * j16 + 2 * j], acc[16 * j16 + 2 * j + 1]);
-          pk.v[j] = *reinterpret_cast<uint32_t*>(&h);
+          for (int j = 0; j < 8; ++j) pk.v[j] = __float_as_uint(acc[8 * j8 + j]);
+          for (int cp = 0; cp < copies; ++cp) st_global_256(dst + cp * copy_stride + 8 * j8, pk);
         }
-        for (int cp = 0; cp < copies; ++cp) st_global_256(dst + cp * copy_stride + 16 * j16, pk);
+      } else {
+#pragma unroll
+        for (int j16 = 0; j16 < 4; ++j16) {   // whole 32-byte sectors per store
+          u32x8 pk;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(acc[16 * j16 + 2 * j], acc[16 * j16 + 2 * j + 1]);
+            pk.v[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          for (int cp = 0; cp < copies; ++cp) st_global_256(dst + cp * copy_stride + 16 * j16, pk);
+        }
       }
     }
   }
@@ -217,8 +229,12 @@ int inconv_launch(const rd_op_inconv& op, cudaStream_t st) {
   RD_REQUIRE(static_cast<size_t>(op.B2) * op.H * op.W < (1u << 31), "in_conv: batch too large");
   size_t blocks = (total + 255) / 256;
   if (blocks > static_cast<size_t>(kNumSMs) * 16) blocks = static_cast<size_t>(kNumSMs) * 16;
-  in_conv_kernel<<<static_cast<unsigned>(blocks), 256, smem, st>>>(op.x, op.w, op.bias, static_cast<__nv_bfloat16*>(op.out),
-                                                                   op.B, op.B2, op.C_in, op.C_out, op.H, op.W);
+  if (op.precision == RD_PREC_F32X3)
+    in_conv_kernel<float><<<static_cast<unsigned>(blocks), 256, smem, st>>>(op.x, op.w, op.bias, static_cast<float*>(op.out),
+                                                                            op.B, op.B2, op.C_in, op.C_out, op.H, op.W);
+  else
+    in_conv_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, smem, st>>>(op.x, op.w, op.bias, static_cast<__nv_bfloat16*>(op.out),
+                                                                                    op.B, op.B2, op.C_in, op.C_out, op.H, op.W);
   return check_launch("in_conv_kernel");
 }
 
@@ -252,11 +268,25 @@ __device__ __forceinline__ void warp_reduce8(float (&v)[8], int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-__global__ void __launch_bounds__(2 * OH_WARPS * 32, 4) out_head_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ gamma,
+// two adjacent channels of one pixel as fp32
+template <typename TI>
+__device__ __forceinline__ float2 oh_load2(const TI* p) {
+  if constexpr (std::is_same<TI, float>::value) {
+    return __ldg(reinterpret_cast<const float2*>(p));
+  } else {
+    const uint32_t xv = __ldg(reinterpret_cast<const uint32_t*>(p));
+    return make_float2(__uint_as_float(xv << 16), __uint_as_float(xv & 0xffff0000u));
+  }
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(2 * OH_WARPS * 32, 4) out_head_kernel(const TI* __restrict__ h, const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, const float* __restrict__ w,
                                                                      const float* __restrict__ bias, const float* __restrict__ cfg_w,
                                                                      float cfg_w_scalar, float* __restrict__ score, int B, int C,
-                                                                     int Cimg, int H, int W, int groups, int cfg, float eps) {
+                                                                     int Cimg, int H, int W, int groups, int cfg, float eps,
+                                                                     const float* __restrict__ sigma_table,
+                                                                     const int32_t* __restrict__ step_ctr) {
   extern __shared__ __align__(16) float sm[];
   const int P = H * W;
   const int npass = cfg ? 2 : 1;
@@ -270,7 +300,7 @@ __global__ void __launch_bounds__(2 * OH_WARPS * 32, 4) out_head_kernel(const __
   const int nslab = C / 64;
   const int ppw = (P + OH_WARPS - 1) / OH_WARPS;       // pixels per warp
   const int px0 = wq * ppw;
-  const __nv_bfloat16* hb = h + static_cast<size_t>(b + pass * B) * P * C;
+  const TI* hb = h + static_cast<size_t>(b + pass * B) * P * C;
   float* qh = q_all + pass * Cimg * P * 9;
 
   for (int slab = 0; slab < nslab; ++slab) {
@@ -281,8 +311,8 @@ __global__ void __launch_bounds__(2 * OH_WARPS * 32, 4) out_head_kernel(const __
     for (int i = 0; i < ppw; ++i) {
       const int px = px0 + i;
       if (px < P) {
-        const uint32_t xv = __ldg(reinterpret_cast<const uint32_t*>(hb + static_cast<size_t>(px) * C + c));
-        const float x0 = __uint_as_float(xv << 16), x1 = __uint_as_float(xv & 0xffff0000u);
+        const float2 xv = oh_load2(hb + static_cast<size_t>(px) * C + c);
+        const float x0 = xv.x, x1 = xv.y;
         s0 += x0; q0 = fmaf(x0, x0, q0);
         s1 += x1; q1 = fmaf(x1, x1, q1);
       }
@@ -324,8 +354,8 @@ __global__ void __launch_bounds__(2 * OH_WARPS * 32, 4) out_head_kernel(const __
       for (int i = 0; i < ppw; ++i) {
         const int px = px0 + i;
         if (px < P) {  // warp-uniform; the second read of the row hits L1/L2
-          const uint32_t xv = __ldg(reinterpret_cast<const uint32_t*>(hb + static_cast<size_t>(px) * C + c));
-          const float y0 = fmaf(__uint_as_float(xv << 16), a0, b0), y1 = fmaf(__uint_as_float(xv & 0xffff0000u), a1, b1);
+          const float2 xv = oh_load2(hb + static_cast<size_t>(px) * C + c);
+          const float y0 = fmaf(xv.x, a0, b0), y1 = fmaf(xv.y, a1, b1);
           const float act0 = silu_acc(y0), act1 = silu_acc(y1);
           float v[8];
 #pragma unroll
@@ -349,6 +379,10 @@ __global__ void __launch_bounds__(2 * OH_WARPS * 32, 4) out_head_kernel(const __
   for (int i = threadIdx.x; i < Cimg * P; i += blockDim.x) {
     const int co = i / P, px = i % P, y = px / W, x = px % W;
     float r[2] = {0.0f, 0.0f};
+    // model.scale_by_sigma (ncsnpp.py:350-351): each network output is divided by its sample's sigma before the
+    // guidance combine; inside the sampler every sample shares sigma_table[*step_ctr]
+    const float sig0 = sigma_table ? (step_ctr ? sigma_table[*step_ctr] : sigma_table[b]) : 1.0f;
+    const float sig1 = sigma_table ? (step_ctr ? sig0 : sigma_table[b + B]) : 1.0f;
     for (int ps = 0; ps < npass; ++ps) {
       float acc = bias[co];
       const float* qq = q_all + (ps * Cimg + co) * P * 9;
@@ -361,7 +395,7 @@ __global__ void __launch_bounds__(2 * OH_WARPS * 32, 4) out_head_kernel(const __
           acc += qq[(yy * W + xx) * 9 + dy * 3 + dx];
         }
       }
-      r[ps] = acc;
+      r[ps] = sigma_table ? __fdiv_rn(acc, ps ? sig1 : sig0) : acc;
     }
     float v = r[0];
     if (npass == 2) {
@@ -380,9 +414,15 @@ int outhead_launch(const rd_op_outhead& op, cudaStream_t st) {
   const int P = op.H * op.W;
   const int smem = (2 * op.C_img * P * 9 + 2 * OH_WARPS * op.C * 2 + 2 * op.groups * 2) * 4;
   RD_REQUIRE(smem <= 48 * 1024, "out_head: image too large for shared memory");
-  out_head_kernel<<<op.B, (op.cfg ? 2 : 1) * OH_WARPS * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(op.h), op.gamma, op.beta, op.w, op.bias,
-                                                  op.cfg_w, op.cfg_w_scalar, op.score, op.B, op.C, op.C_img, op.H, op.W,
-                                                  op.groups, op.cfg, op.eps);
+  const int threads = (op.cfg ? 2 : 1) * OH_WARPS * 32;
+  if (op.precision == RD_PREC_F32X3)
+    out_head_kernel<float><<<op.B, threads, smem, st>>>(static_cast<const float*>(op.h), op.gamma, op.beta, op.w, op.bias, op.cfg_w,
+                                                        op.cfg_w_scalar, op.score, op.B, op.C, op.C_img, op.H, op.W, op.groups, op.cfg,
+                                                        op.eps, op.sigma_table, op.step_ctr);
+  else
+    out_head_kernel<__nv_bfloat16><<<op.B, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(op.h), op.gamma, op.beta, op.w, op.bias,
+                                                                op.cfg_w, op.cfg_w_scalar, op.score, op.B, op.C, op.C_img, op.H, op.W,
+                                                                op.groups, op.cfg, op.eps, op.sigma_table, op.step_ctr);
   return check_launch("out_head_kernel");
 }
 

@@ -12,8 +12,9 @@ import torch
 import torch.nn as nn
 
 from . import layers, layerspp, utils
-from rdb200.engine import ForwardEngine, SamplerEngine, spec_from_config
+from rdb200.engine import PRECISIONS, ForwardEngine, SamplerEngine, spec_from_config
 from rdb200.pack import PackedWeights
+from rdb200 import ops as _rd_ops
 
 ResnetBlockDDPM = layerspp.ResnetBlockDDPMpp
 conv3x3 = layerspp.conv3x3
@@ -103,7 +104,9 @@ class NCSNpp(nn.Module):
         # ---- B200 execution state (not part of the state_dict)
         self._rd_spec = spec_from_config(config)
         self._rd_packed = None
-        self._rd_fingerprint = None
+        self._rd_token = None          # content checksum of the parameters the packed weights were made from
+        self._rd_segments = None       # (data_ptr key, device segment table, device result) of the checksum kernel
+        self._rd_frozen = 0            # > 0 inside a sampling loop: parameters cannot change, skip the check
         self._rd_forward_engines = {}
         self._rd_sampler_engines = {}
 
@@ -111,31 +114,71 @@ class NCSNpp(nn.Module):
     def _rd_device(self):
         return self.input_conv.weight.device
 
-    def _rd_current_fingerprint(self):
-        # EMA copy_to/restore write through `.data`, which does not bump tensor versions, so weight
-        # changes are detected from the values themselves (one fused reduction, ~260 tensors).
+    @property
+    def rd_precision(self):
+        return self._rd_spec.precision
+
+    def rd_set_precision(self, precision):
+        """'bf16' (default): bf16 activations / operands.  'fp32': the fp32-class plan (fp32 activations, split-bf16
+        tensor-core operands, fp32 attention core).  Also settable as config.model.rd_precision / RDB200_PRECISION."""
+        if precision not in PRECISIONS:
+            raise ValueError(f"unknown precision {precision!r}: expected one of {sorted(PRECISIONS)}")
+        if precision != self._rd_spec.precision:
+            self._rd_spec.precision = precision
+            self._rd_packed, self._rd_token = None, None
+            self._rd_forward_engines.clear()
+            self._rd_sampler_engines.clear()
+        return self
+
+    def _rd_weights_token(self):
+        """64-bit checksum of every parameter's values and positions: one kernel launch + an 8-byte read (EMA
+        copy_to / restore and load_state_dict write through `.data` / copy_ in place, which no version counter of
+        the Parameter objects records)."""
         ps = [p.detach() for p in self.parameters()]
-        return torch.stack(torch._foreach_norm(ps))
+        key = tuple((p.data_ptr(), p.numel()) for p in ps)
+        if self._rd_segments is None or self._rd_segments[0] != key:
+            for p in ps:
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError('NCSNpp (B200) expects contiguous float32 parameters')
+            self._rd_segments = (key,) + _rd_ops.checksum_segments(ps)
+        return _rd_ops.checksum(self._rd_segments[1], self._rd_segments[2])
 
     @torch.no_grad()
     def rd_sync_weights(self, force=False):
-        """(Re)pack the parameters into kernel layouts if they changed; returns True when repacked."""
+        """(Re)pack the parameters into kernel layouts if their content changed; returns True when repacked."""
         dev = self._rd_device()
         if dev.type != 'cuda':
             raise RuntimeError('NCSNpp (B200) has no CPU path: move the model to a CUDA device')
-        fp = self._rd_current_fingerprint()
-        if (not force and self._rd_packed is not None and self._rd_fingerprint is not None
-                and self._rd_fingerprint.device == fp.device and torch.equal(fp, self._rd_fingerprint)):
+        if self._rd_frozen and self._rd_packed is not None and not force:
             return False
-        if self._rd_packed is None or self._rd_packed.device != dev:
-            self._rd_packed = PackedWeights(dev)
+        token = self._rd_weights_token()
+        if not force and self._rd_packed is not None and self._rd_packed.device == dev and token == self._rd_token:
+            return False
+        x3 = self._rd_spec.precision == 'fp32'
+        if self._rd_packed is None or self._rd_packed.device != dev or self._rd_packed.x3 != x3:
+            self._rd_packed = PackedWeights(dev, x3=x3)
             self._rd_forward_engines.clear()
             self._rd_sampler_engines.clear()
         self._rd_packed.update(self.state_dict(), self._rd_spec.res_blocks(), self._rd_spec.attn_blocks())
-        self._rd_fingerprint = fp
+        self._rd_token = token
         for eng in self._rd_sampler_engines.values():
             eng.refresh_tables()
         return True
+
+    def rd_freeze_weights(self):
+        """Context manager for loops that call the model many times while nothing can touch its parameters (the
+        generic update_fn sampler loop): the content check runs once on entry instead of once per call."""
+        model = self
+
+        class _Frozen:
+            def __enter__(self_inner):
+                model.rd_sync_weights()
+                model._rd_frozen += 1
+
+            def __exit__(self_inner, *exc):
+                model._rd_frozen -= 1
+                return False
+        return _Frozen()
 
     # ------------------------------------------------------------------ reference call surface
     def forward(self, x, time_cond, class_labels=None):

@@ -41,6 +41,7 @@ SIGNATURES = {
     "rd_dsm_reduce_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_size_t, C.c_size_t, C.c_int, c_vp]),
     "rd_pf_drift_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_float, C.c_float, c_vp, C.c_size_t, C.c_size_t, c_vp]),
     "rd_gto_halo_decode_f32": (C.c_int, [c_vp, c_vp, C.c_size_t, C.c_size_t, c_vp, c_vp]),
+    "rd_gto_halo_encode_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, C.c_float, c_vp]),
     "rd_plan_create": (C.c_int, [C.POINTER(c_vp)]),
     "rd_plan_add": (C.c_int, [c_vp, c_vp]),
     "rd_plan_size": (C.c_int, [c_vp]),
@@ -48,7 +49,7 @@ SIGNATURES = {
     "rd_plan_run_range": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "rd_plan_destroy": (C.c_int, [c_vp]),
     "rd_conv_launch_info": (C.c_int, [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    "rd_conv_set_trace": (C.c_int, [c_vp, C.c_int]),
+    "rd_checksum_f32": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
     "rd_sampler_create": (C.c_int, [c_vp, C.POINTER(c_vp)]),
     "rd_sampler_run": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "rd_sampler_launches_per_iter": (C.c_int, [c_vp]),

@@ -2,6 +2,7 @@
 tests/test_abi.py cross-checks sizeof/offsetof against a tiny C program compiled from the header)."""
 import ctypes as C
 
+RD_PREC_BF16, RD_PREC_F32X3 = 0, 1
 RD_OP_CONV, RD_OP_ATTN_CORE, RD_OP_TEMB, RD_OP_IN_CONV, RD_OP_OUT_HEAD, RD_OP_ATTN_BLOCK = 1, 2, 3, 4, 5, 6
 
 i32 = C.c_int32
@@ -25,11 +26,11 @@ class OpConv(C.Structure):
         ("H_out", i32), ("W_out", i32), ("ntaps", i32), ("C_out", i32), ("gn_groups", i32), ("gn_silu", i32),
         ("gn_eps", C.c_float), ("gn_gamma", vp), ("gn_beta", vp), ("w", vp), ("bias", vp), ("tproj", vp),
         ("tproj_stride", i32), ("tproj_off", i32), ("tproj_wrap", i32), ("residual", vp), ("out_scale", C.c_float), ("out", vp),
-        ("B2", i32), ("samples_per_cta", i32)]
+        ("B2", i32), ("samples_per_cta", i32), ("precision", i32), ("out_stride", i32)]
 
 
 class OpAttn(C.Structure):
-    _fields_ = [("qkv", vp), ("out", vp), ("B2", i32), ("T", i32), ("C", i32)]
+    _fields_ = [("qkv", vp), ("out", vp), ("B2", i32), ("T", i32), ("C", i32), ("precision", i32)]
 
 
 class OpAttnBlock(C.Structure):
@@ -46,13 +47,14 @@ class OpTemb(C.Structure):
 
 class OpInConv(C.Structure):
     _fields_ = [("x", vp), ("w", vp), ("bias", vp), ("out", vp), ("B", i32), ("B2", i32), ("C_in", i32),
-                ("C_out", i32), ("H", i32), ("W", i32)]
+                ("C_out", i32), ("H", i32), ("W", i32), ("precision", i32)]
 
 
 class OpOutHead(C.Structure):
     _fields_ = [("h", vp), ("gamma", vp), ("beta", vp), ("w", vp), ("bias", vp), ("cfg_w", vp),
                 ("cfg_w_scalar", C.c_float), ("score", vp), ("B", i32), ("B2", i32), ("C", i32), ("C_img", i32),
-                ("H", i32), ("W", i32), ("groups", i32), ("cfg", i32), ("eps", C.c_float)]
+                ("H", i32), ("W", i32), ("groups", i32), ("cfg", i32), ("eps", C.c_float), ("precision", i32),
+                ("sigma_table", vp), ("step_ctr", vp)]
 
 
 class _OpUnion(C.Union):

@@ -34,6 +34,10 @@ class GtoHaloConstants:
         n_ctrl = self.n_variables - 1 - 3 - 3
         if n_ctrl < 0:
             raise ValueError("n_variables must be at least 7")
+        if n_ctrl % 3 != 0:
+            # the reference converts whole (ux, uy, uz) triplets and leaves stragglers in cartesian form in the row
+            # (gto_halo_benchmarking.py:295-298, :314); the kernel's row layout has no slot for them
+            raise ValueError(f"n_variables - 7 = {n_ctrl} control values do not form whole (ux, uy, uz) triplets")
         return GtoHaloCodec(
             self.data_mean, self.data_std,
             self.min_shooting_time, self.max_shooting_time - self.min_shooting_time,
@@ -46,8 +50,7 @@ class GtoHaloConstants:
 
 def gto_halo_decode(samples: torch.Tensor, consts: GtoHaloConstants = GtoHaloConstants()) -> torch.Tensor:
     """samples: [N, ...] fp32 CUDA latents straight from the sampler (e.g. [N,1,9,9] or [N,1,8,9]);
-    returns [N, 7 + 3*n_triplets] physical variables on the same device.  Control variables that do not
-    fill a whole (ux,uy,uz) triplet are dropped, as in the reference (:295-298)."""
+    returns [N, 7 + 3*n_triplets] physical variables on the same device (n_variables - 7 must be a multiple of 3)."""
     x = require_cuda_f32(samples, "samples")
     n = x.shape[0]
     stride = x.numel() // max(n, 1)
@@ -59,3 +62,22 @@ def gto_halo_decode(samples: torch.Tensor, consts: GtoHaloConstants = GtoHaloCon
     check(lib().rd_gto_halo_decode_f32(ptr(x), ptr(out), n, stride, C.byref(cs), stream_ptr(x.device)),
           "rd_gto_halo_decode_f32")
     return out
+
+
+def gto_halo_encode(raw: torch.Tensor, image_size: int = 9, image_width: int = None,
+                    consts: GtoHaloConstants = GtoHaloConstants()):
+    """Dataset rows -> latents, the inverse direction (reference datasets.GTOHaloImageDataset.__getitem__,
+    datasets.py:88-98): raw [N, n_values <= H*W] fp32 CUDA -> (latents [N, 1, H, W], labels [N, 1]); rows are zero-padded
+    to H*W and z-scored with the data mean / std, the label is the un-normalised first value."""
+    x = require_cuda_f32(raw, "raw")
+    if x.dim() != 2:
+        raise ValueError("raw must be [N, n_values]")
+    W = image_size if image_width is None else image_width
+    n, n_in, n_lat = x.shape[0], x.shape[1], image_size * W
+    if n_in > n_lat:
+        raise ValueError(f"{n_in} values per row do not fit a {image_size}x{W} latent")
+    lat = torch.empty((n, 1, image_size, W), dtype=torch.float32, device=x.device)
+    lab = torch.empty((n, 1), dtype=torch.float32, device=x.device)
+    check(lib().rd_gto_halo_encode_f32(ptr(x), ptr(lat), ptr(lab), n, n_in, n_lat, consts.data_mean, consts.data_std,
+                                       stream_ptr(x.device)), "rd_gto_halo_encode_f32")
+    return lat, lab

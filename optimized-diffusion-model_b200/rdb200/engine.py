@@ -17,7 +17,9 @@ import torch
 
 from . import cdefs as D
 from ._lib import check, lib, stream_ptr
-from .pack import PackedWeights
+from .pack import PackedWeights, n_slices
+
+PRECISIONS = {"bf16": D.RD_PREC_BF16, "fp32": D.RD_PREC_F32X3}
 
 
 @dataclass
@@ -32,6 +34,7 @@ class NetSpec:
     conditional: bool = True
     skip_rescale: bool = True
     scale_by_sigma: bool = False
+    precision: str = "bf16"   # "bf16" | "fp32" (fp32-class: fp32 activations, split-bf16 tensor-core operands)
 
     @property
     def levels(self) -> int:
@@ -69,19 +72,29 @@ class NetSpec:
         return out
 
 
+def precision_from_config(config) -> str:
+    """`config.model.rd_precision` ("bf16" default | "fp32"); the environment variable RDB200_PRECISION overrides it
+    (so an unmodified consumer script can be switched without touching its YAML)."""
+    import os
+    prec = os.environ.get("RDB200_PRECISION") or getattr(config.model, "rd_precision", "bf16")
+    if prec not in PRECISIONS:
+        raise ValueError(f"unknown rd_precision {prec!r}: expected one of {sorted(PRECISIONS)}")
+    return prec
+
+
 def spec_from_config(config) -> NetSpec:
     m = config.model
-    return NetSpec(channels=m.channels, image_size=m.image_size, nf=m.nf, ch_mult=tuple(m.ch_mult),
+    return NetSpec(precision=precision_from_config(config), channels=m.channels, image_size=m.image_size, nf=m.nf, ch_mult=tuple(m.ch_mult),
                    num_res_blocks=m.num_res_blocks, attn_resolutions=tuple(m.attn_resolutions),
                    num_classes=getattr(m, "num_classes", 1), conditional=m.conditional,
                    skip_rescale=m.skip_rescale, scale_by_sigma=getattr(m, "scale_by_sigma", False))
 
 
 class _Act:
-    """An NHWC bf16 activation buffer [B2, H, W, C]."""
+    """An NHWC activation buffer [B2, H, W, C] (bf16, or fp32 in the fp32-class plan)."""
 
-    def __init__(self, B2, H, W, Cc, device):
-        self.t = torch.empty((B2, H, W, Cc), dtype=torch.bfloat16, device=device)
+    def __init__(self, B2, H, W, Cc, device, dtype=torch.bfloat16):
+        self.t = torch.empty((B2, H, W, Cc), dtype=dtype, device=device)
         self.H, self.W, self.C = H, W, Cc
 
     @property
@@ -100,6 +113,10 @@ class Engine:
     def __init__(self, spec: NetSpec, weights: PackedWeights, B: int, H: int, W: int, cfg: bool, device):
         self.spec, self.w, self.B, self.H, self.W, self.cfg = spec, weights, B, H, W, cfg
         self.device = torch.device(device)
+        self.prec = PRECISIONS[spec.precision]
+        if bool(weights.x3) != (self.prec == D.RD_PREC_F32X3):
+            raise RuntimeError("packed weights and engine precision disagree")
+        self.act_dtype = torch.float32 if self.prec == D.RD_PREC_F32X3 else torch.bfloat16
         self.B2 = 2 * B if cfg else B
         nc = max(spec.num_classes, 1)
         dev = self.device
@@ -123,13 +140,14 @@ class Engine:
         self.op_names: List[str] = []
         self.op_kinds: Dict[str, str] = {}
         self.conv_flops_per_sample = 0.0  # algorithmic 2*M*N*K of the tcgen05 launches, valid pixels only
+        self.attn_flops_per_sample = 0.0  # QK^T + PV of the stand-alone attention core launches
         self.tensors: Dict[str, _Act] = {}
         self._sampler = None
         self._built_for_table = None
 
     # ------------------------------------------------------------------ plan construction
     def _act(self, H, W, Cc) -> _Act:
-        a = _Act(self.B2, H, W, Cc, self.device)
+        a = _Act(self.B2, H, W, Cc, self.device, self.act_dtype)
         self.acts.append(a)
         return a
 
@@ -146,27 +164,31 @@ class Engine:
         else:
             Ho, Wo = H_in, W_in
         out = self._act(Ho, Wo, C_out)
-        op = D.Op()
-        op.kind = D.RD_OP_CONV
-        c = op.u.conv
-        c.nsrc = len(srcs)
-        for i, s in enumerate(srcs):
-            c.src[i].ptr, c.src[i].C, c.src[i].Hs, c.src[i].Ws = s.ptr, s.C, s.H, s.W
-        c.H_in, c.W_in, c.pad, c.stride, c.H_out, c.W_out = H_in, W_in, pad, stride, Ho, Wo
-        c.ntaps, c.C_out = ntaps, C_out
-        if gn is not None:
-            cin = sum(s.C for s in srcs)
-            c.gn_groups, c.gn_silu, c.gn_eps = min(cin // 4, 32), silu, 1e-6
-            c.gn_gamma, c.gn_beta = self.w.ptr(gn + ".weight"), self.w.ptr(gn + ".bias")
-        c.w, c.bias = self.w.ptr(wname), self.w.ptr(bias)
-        if tproj_off is not None:
-            c.tproj, c.tproj_stride, c.tproj_off = self.tproj.data_ptr(), self.w.n_dense_out, tproj_off
-            c.tproj_wrap = self.B if self.temb_rows == self.B + 1 else 0
-        if residual is not None:
-            c.residual = residual.ptr
-        c.out_scale, c.out, c.B2, c.samples_per_cta = out_scale, out.ptr, self.B2, 0
+        esz = out.t.element_size()
+        # a layer wider than one launch is issued as channel slices: same inputs, the slice's own packed filter, and
+        # out / residual / bias / temb offset advanced to the slice's first channel (include/rdb200.h `out_stride`)
+        for si, (n0, n) in enumerate(n_slices(C_out)):
+            op = D.Op()
+            op.kind = D.RD_OP_CONV
+            c = op.u.conv
+            c.nsrc = len(srcs)
+            for i, s in enumerate(srcs):
+                c.src[i].ptr, c.src[i].C, c.src[i].Hs, c.src[i].Ws = s.ptr, s.C, s.H, s.W
+            c.H_in, c.W_in, c.pad, c.stride, c.H_out, c.W_out = H_in, W_in, pad, stride, Ho, Wo
+            c.ntaps, c.C_out, c.out_stride, c.precision = ntaps, n, C_out, self.prec
+            if gn is not None:
+                cin = sum(s.C for s in srcs)
+                c.gn_groups, c.gn_silu, c.gn_eps = min(cin // 4, 32), silu, 1e-6
+                c.gn_gamma, c.gn_beta = self.w.ptr(gn + ".weight"), self.w.ptr(gn + ".bias")
+            c.w, c.bias = self.w.ptr(wname + (f".s{si}" if si else "")), self.w.ptr(bias) + 4 * n0
+            if tproj_off is not None:
+                c.tproj, c.tproj_stride, c.tproj_off = self.tproj.data_ptr(), self.w.n_dense_out, tproj_off + n0
+                c.tproj_wrap = self.B if self.temb_rows == self.B + 1 else 0
+            if residual is not None:
+                c.residual = residual.ptr + esz * n0
+            c.out_scale, c.out, c.B2, c.samples_per_cta = out_scale, out.ptr + esz * n0, self.B2, 0
+            self._add(op, name if si == 0 else f"{name}#s{si}")
         self.conv_flops_per_sample += 2.0 * Ho * Wo * C_out * sum(s.C for s in srcs) * ntaps
-        self._add(op, name)
         self.tensors[name] = out
         return out
 
@@ -185,13 +207,12 @@ class Engine:
                           residual=short, out_scale=rs)
 
     def _attn(self, p: str, x: _Act) -> _Act:
-        """AttnBlockpp (layerspp.py:80-96).  Default: ONE fused kernel (GN, q/k/v, softmax(qk^T)v, projection, skip).
-        RD_ATTN_FUSED=0 selects the three-launch path (tcgen05 qkv projection, attention core, tcgen05 output
-        projection) that the fused kernel replaced; it is kept for A/B measurements."""
-        import os
+        """AttnBlockpp (layerspp.py:80-96).  bf16 plan at the GTO-Halo shapes (C = 64, T <= 128): ONE fused kernel (GN,
+        q/k/v, softmax(qk^T)v, projection, skip).  Otherwise (fp32-class plan, or C5's T = 256 / C = 256): GroupNorm +
+        q|k|v projection on tcgen05, the flash-style attention core, output projection + skip on tcgen05."""
         rs = float(1.0 / np.sqrt(2.0)) if self.spec.skip_rescale else 1.0
         Cc = x.C
-        if os.environ.get("RD_ATTN_FUSED", "1") != "0" and Cc == 64 and x.H * x.W <= 128:
+        if self.prec == D.RD_PREC_BF16 and Cc == 64 and x.H * x.W <= 128:
             out = self._act(x.H, x.W, Cc)
             op = D.Op()
             op.kind = D.RD_OP_ATTN_BLOCK
@@ -210,8 +231,10 @@ class Engine:
         op = D.Op()
         op.kind = D.RD_OP_ATTN_CORE
         op.u.attn.qkv, op.u.attn.out, op.u.attn.B2, op.u.attn.T, op.u.attn.C = qkv.ptr, a.ptr, self.B2, x.H * x.W, Cc
+        op.u.attn.precision = self.prec
         self._add(op, p + ".core")
         self.tensors[p + ".core"] = a
+        self.attn_flops_per_sample += 4.0 * (x.H * x.W) ** 2 * Cc
         return self._conv(p, [a], x.H, x.W, Cc, p + ".proj.w", p + ".proj.bias", ntaps=1, pad=0, residual=x,
                           out_scale=rs)
 
@@ -236,6 +259,7 @@ class Engine:
         ic = op_in.u.inconv
         ic.x, ic.w, ic.bias, ic.out = self.x.data_ptr(), w.ptr("input_conv.weight"), w.ptr("input_conv.bias"), h.ptr
         ic.B, ic.B2, ic.C_in, ic.C_out, ic.H, ic.W = self.B, self.B2, sp.channels, nf, self.H, self.W
+        ic.precision = self.prec
         self._in_op = op_in
         self._pending = [("temb", self._temb_op), ("input_conv", op_in)]
         self.tensors["input_conv"] = h
@@ -298,8 +322,15 @@ class Engine:
         o.cfg_w, o.cfg_w_scalar, o.score = (self.cfg_w.data_ptr() if self.cfg else None), 0.0, self.score.data_ptr()
         o.B, o.B2, o.C, o.C_img, o.H, o.W = self.B, self.B2, h.C, sp.channels, self.H, self.W
         o.groups, o.cfg, o.eps = min(h.C // 4, 32), (1 if self.cfg else 0), 1e-6
+        o.precision = self.prec
+        if sp.scale_by_sigma:  # ncsnpp.py:350-351: h / sigma, folded into the output head
+            o.sigma_table, o.step_ctr = self._sigma_source()
         self._add(op, "out_head")
         self.n_ops = lib().rd_plan_size(self.plan)
+
+    def _sigma_source(self):
+        """(sigma table pointer, step counter pointer or None) for scale_by_sigma; set by the subclasses."""
+        raise NotImplementedError
 
     # ------------------------------------------------------------------ execution
     def run_plan(self):
@@ -327,24 +358,26 @@ class ForwardEngine(Engine):
 
     def __init__(self, spec, weights, B, H, W, device):
         super().__init__(spec, weights, B, H, W, cfg=False, device=device)
+        self.sigma_rows = torch.ones((self.B2,), dtype=torch.float32, device=self.device)
         self.build()
         table = torch.zeros((self.B2, self.temb_dim), dtype=torch.float32, device=self.device)
         self.finalize(table, use_row_idx=True)
+
+    def _sigma_source(self):
+        return self.sigma_rows.data_ptr(), None  # one sigma per sample
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor, sigma: torch.Tensor, labels: Optional[torch.Tensor]) -> torch.Tensor:
         self.x.copy_(x.reshape(self.x.shape))
         self.time_table.copy_(self.w.time_rows(sigma.reshape(-1)))
+        self.sigma_rows.copy_(sigma.reshape(-1))
         if self.spec.conditional:
             if labels is None:
                 raise TypeError("conditional NCSNpp needs class_labels (the reference fails the same way, "
                                 "ncsnpp.py:262)")
             self.labels2.copy_(labels.reshape(self.labels2.shape))
         self.run_plan()
-        out = self.score.clone()
-        if self.spec.scale_by_sigma:
-            out = out / sigma.view(-1, 1, 1, 1)
-        return out
+        return self.score.clone()
 
 
 class SamplerEngine(Engine):
@@ -366,6 +399,9 @@ class SamplerEngine(Engine):
         self._tape = None
         self._desc = None
         self.stream = torch.cuda.Stream(device=self.device)
+
+    def _sigma_source(self):
+        return self.sigma_tab.data_ptr(), self.step_ctr.data_ptr()  # every sample shares sigma_i inside the sampler
 
     def refresh_tables(self):
         """Re-tabulate the batch-invariant time embedding after a weight change."""

@@ -171,3 +171,25 @@ def pf_drift(x: torch.Tensor, score: torch.Tensor, g, moll: float) -> torch.Tens
     check(lib().rd_pf_drift_f32(ptr(x), ptr(score), gp, gs, float(moll), ptr(out), B, x.numel() // max(B, 1),
                                 stream_ptr(x.device)), "rd_pf_drift_f32")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parameter change detection (csrc/weights.cu)
+_SEG = 1 << 16
+
+
+def checksum_segments(tensors):
+    """Device segment table [(address, first flat index, count)] over `tensors` (contiguous fp32 CUDA) + result slot."""
+    rows, first = [], 0
+    for t in tensors:
+        n, base = t.numel(), t.data_ptr()
+        for o in range(0, n, _SEG):
+            rows.append((base + 4 * o, first + o, min(_SEG, n - o)))
+        first += n
+    dev = tensors[0].device
+    return (torch.tensor(rows, dtype=torch.int64).to(dev), torch.zeros((1,), dtype=torch.int64, device=dev))
+
+
+def checksum(segs: torch.Tensor, out: torch.Tensor) -> int:
+    check(lib().rd_checksum_f32(segs.data_ptr(), segs.shape[0], out.data_ptr(), stream_ptr(segs.device)), "rd_checksum_f32")
+    return int(out.item())

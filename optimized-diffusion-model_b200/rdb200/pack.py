@@ -13,20 +13,38 @@ from typing import Dict, List
 import torch
 
 
-def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
-    """[C_out, C_in, 3, 3] fp32 -> [C_in/64, 9, 8, C_out, 8] bf16 (tap = dy*3+dx)."""
+MAX_N_PER_LAUNCH = 128  # output channels of one conv launch; wider layers are issued as channel slices (engine._conv)
+
+
+def n_slices(c_out: int):
+    """[(first channel, width)] of the launches that make up a layer with `c_out` output channels."""
+    return [(n0, min(MAX_N_PER_LAUNCH, c_out - n0)) for n0 in range(0, c_out, MAX_N_PER_LAUNCH)]
+
+
+def _planes(t: torch.Tensor, x3: bool) -> torch.Tensor:
+    """[chunk, tap, 8, n, 8] fp32 -> bf16 operand image; fp32-class mode: [chunk, tap, 2 (hi|lo), 8, n, 8] with
+    w ~= hi + lo (both bf16, round to nearest)."""
+    hi = t.to(torch.bfloat16)
+    if not x3:
+        return hi.contiguous()
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo], dim=2).contiguous()
+
+
+def pack_conv3x3(w: torch.Tensor, x3: bool = False) -> torch.Tensor:
+    """[C_out, C_in, 3, 3] fp32 -> [C_in/64, 9, (2,) 8, C_out, 8] bf16 (tap = dy*3+dx)."""
     co, ci = w.shape[0], w.shape[1]
     assert ci % 64 == 0, "C_in must be a multiple of 64"
     t = w.permute(1, 2, 3, 0).reshape(ci // 64, 8, 8, 9, co)  # [chunk, kc, j, tap, n]
-    return t.permute(0, 3, 1, 4, 2).contiguous().to(torch.bfloat16)
+    return _planes(t.permute(0, 3, 1, 4, 2), x3)
 
 
-def pack_1x1(W: torch.Tensor) -> torch.Tensor:
-    """NIN weight [C_in, C_out] fp32 -> [C_in/64, 1, 8, C_out, 8] bf16."""
+def pack_1x1(W: torch.Tensor, x3: bool = False) -> torch.Tensor:
+    """NIN weight [C_in, C_out] fp32 -> [C_in/64, 1, (2,) 8, C_out, 8] bf16."""
     ci, co = W.shape
     assert ci % 64 == 0
     t = W.reshape(ci // 64, 8, 8, 1, co)  # [chunk, kc, j, tap, n]
-    return t.permute(0, 3, 1, 4, 2).contiguous().to(torch.bfloat16)
+    return _planes(t.permute(0, 3, 1, 4, 2), x3)
 
 
 def pad_rows(w: torch.Tensor, ld: int) -> torch.Tensor:
@@ -36,27 +54,18 @@ def pad_rows(w: torch.Tensor, ld: int) -> torch.Tensor:
     return out
 
 
-def conv_weight_replicas() -> int:
-    """Copies of every packed conv filter (must match RD_CONV_WREPS as read by csrc/conv_gemm.cu)."""
-    import os
-    return max(1, min(16, int(os.environ.get("RD_CONV_WREPS", "1"))))
-
-
 class PackedWeights:
     """Device-resident packed parameters of one NCSNpp instance."""
 
-    def __init__(self, device):
+    def __init__(self, device, x3: bool = False):
         self.device = device
+        self.x3 = bool(x3)  # fp32-class plan: conv / NIN filters as bf16 hi + lo planes
         self.t: Dict[str, torch.Tensor] = {}
         self.dense_offsets: Dict[str, int] = {}
         self.n_dense_out = 0
 
     def _put(self, name: str, value: torch.Tensor):
         value = value.detach().to(self.device)
-        if name.endswith(".w") and conv_weight_replicas() > 1:
-            # streamed filters: identical copies at distinct addresses, CTA i reads copy i % R (conv_gemm.cu), which
-            # spreads the 148 CTAs' simultaneous requests for one slab over R times as many L2 lines
-            value = value.unsqueeze(0).repeat((conv_weight_replicas(),) + (1,) * value.dim())
         if name in self.t:
             if self.t[name].shape != value.shape or self.t[name].dtype != value.dtype:
                 raise RuntimeError(f"packed tensor {name} changed shape/dtype; rebuild the engine")
@@ -66,6 +75,16 @@ class PackedWeights:
 
     def ptr(self, name: str) -> int:
         return self.t[name].data_ptr()
+
+    def _put_conv(self, name: str, w: torch.Tensor):
+        """3x3 filter [C_out, C_in, 3, 3] -> one packed tensor per channel slice: `name.w` (first / only), `name.w.s1`, ..."""
+        for i, (n0, n) in enumerate(n_slices(w.shape[0])):
+            self._put(name + ".w" + (f".s{i}" if i else ""), pack_conv3x3(w[n0:n0 + n], self.x3))
+
+    def _put_nin(self, name: str, W: torch.Tensor):
+        """NIN weight [C_in, C_out], sliced the same way."""
+        for i, (n0, n) in enumerate(n_slices(W.shape[1])):
+            self._put(name + ".w" + (f".s{i}" if i else ""), pack_1x1(W[:, n0:n0 + n], self.x3))
 
     @torch.no_grad()
     def update(self, sd: Dict[str, torch.Tensor], res_blocks: List[str], attn_blocks: List[str]):
@@ -87,10 +106,10 @@ class PackedWeights:
                 self._put(f"{p}.{gn}.weight", f32(sd[f"{p}.{gn}.weight"]))
                 self._put(f"{p}.{gn}.bias", f32(sd[f"{p}.{gn}.bias"]))
             for cv in ("Conv_0", "Conv_1"):
-                self._put(f"{p}.{cv}.w", pack_conv3x3(f32(sd[f"{p}.{cv}.weight"])))
+                self._put_conv(f"{p}.{cv}", f32(sd[f"{p}.{cv}.weight"]))
                 self._put(f"{p}.{cv}.bias", f32(sd[f"{p}.{cv}.bias"]))
             if f"{p}.NIN_0.W" in sd:
-                self._put(f"{p}.NIN_0.w", pack_1x1(f32(sd[f"{p}.NIN_0.W"])))
+                self._put_nin(f"{p}.NIN_0", f32(sd[f"{p}.NIN_0.W"]))
                 self._put(f"{p}.NIN_0.bias", f32(sd[f"{p}.NIN_0.b"]))
             w = f32(sd[f"{p}.Dense_0.weight"])
             self.dense_offsets[p] = off
@@ -104,19 +123,20 @@ class PackedWeights:
             self._put(f"{p}.GroupNorm_0.weight", f32(sd[f"{p}.GroupNorm_0.weight"]))
             self._put(f"{p}.GroupNorm_0.bias", f32(sd[f"{p}.GroupNorm_0.bias"]))
             qkv = torch.cat([f32(sd[f"{p}.NIN_{j}.W"]) for j in range(3)], dim=1)  # [C, 3C]
-            self._put(f"{p}.qkv.w", pack_1x1(qkv))
+            self._put_nin(f"{p}.qkv", qkv)
             self._put(f"{p}.qkv.bias", torch.cat([f32(sd[f"{p}.NIN_{j}.b"]) for j in range(3)]))
-            self._put(f"{p}.proj.w", pack_1x1(f32(sd[f"{p}.NIN_3.W"])))
+            self._put_nin(f"{p}.proj", f32(sd[f"{p}.NIN_3.W"]))
             self._put(f"{p}.proj.bias", f32(sd[f"{p}.NIN_3.b"]))
             # fused attention kernel: weights transposed to [out][in] bf16 rows padded to 72 (conflict-free fragments)
-            self._put(f"{p}.wqkv_t", pad_rows(qkv.t().contiguous(), 72))
-            self._put(f"{p}.wproj_t", pad_rows(f32(sd[f"{p}.NIN_3.W"]).t().contiguous(), 72))
+            if qkv.shape[0] == 64:
+                self._put(f"{p}.wqkv_t", pad_rows(qkv.t().contiguous(), 72))
+                self._put(f"{p}.wproj_t", pad_rows(f32(sd[f"{p}.NIN_3.W"]).t().contiguous(), 72))
             # fused kernel: k / v carry no bias (csrc/attn_core.cu); the value bias reaches the output as b_v @ W_3
             self._put(f"{p}.proj.bias_fused", f32(sd[f"{p}.NIN_3.b"]) + f32(sd[f"{p}.NIN_2.b"]) @ f32(sd[f"{p}.NIN_3.W"]))
         for k in list(sd.keys()):
             if (k.startswith("downsample.") or k.startswith("upsample.")) and k.endswith(".Conv_0.weight"):
                 p = k[: -len(".weight")]
-                self._put(p + ".w", pack_conv3x3(f32(sd[k])))
+                self._put_conv(p, f32(sd[k]))
                 self._put(p + ".bias", f32(sd[p + ".bias"]))
 
     @torch.no_grad()

@@ -14,6 +14,7 @@ B200 execution:
     read on the device, noise from an in-kernel Philox stream (or an injected tape for parity).
 """
 import abc
+import contextlib
 
 import numpy as np
 import torch
@@ -170,8 +171,6 @@ def _native_engine(model, sde, shape, predictor, corrector, snr, n_steps, eps, d
         n_corr = 0
     else:
         return None
-    if n_corr > 1:
-        return None
     cfg = class_labels is not None
     if not cfg and getattr(model, 'conditional', False):
         return None  # (the reference crashes here: label_emb(None), ncsnpp.py:262)
@@ -188,7 +187,7 @@ def get_pc_sampler(sde, shape, predictor, corrector, denoiser, snr, n_steps=1, e
 
         `z` is accepted and ignored exactly like the reference (the prior is re-drawn, sampling.py:324).
         Extras (keyword-only, not in the reference): `rd_tape` [(N-1)*k, B, C, H, W] replays injected
-        N(0,1) noise (k = 2 with the Langevin corrector, 1 without) for parity runs; `rd_seed` fixes the
+        N(0,1) noise (k = n_steps + 1 with the Langevin corrector, 1 without) for parity runs; `rd_seed` fixes the
         Philox stream; `rd_native=False` forces the generic python loop over `update_fn`.
         """
         if z is None:
@@ -211,13 +210,16 @@ def get_pc_sampler(sde, shape, predictor, corrector, denoiser, snr, n_steps=1, e
             pred, corr = predictor(sde, score_fn), corrector(sde, score_fn, snr, n_steps)
             tape = None if rd_tape is None else list(rd_tape)
             timesteps = torch.linspace(sde.T, eps, sde.N, device=device)
-            for i in range(sde.N - 1):  # the last grid point performs no update (sampling.py:330)
-                vec_t = torch.ones(shape[0], device=device) * timesteps[i]
-                if tape is not None:
-                    x = _tape_iteration(pred, corr, x, vec_t, tape, device)
-                else:
-                    x, _ = corr.update_fn(x, vec_t)
-                    x, _ = pred.update_fn(x, vec_t)
+            # nothing can rewrite the parameters inside this loop: check / pack the weights once, not per call
+            frozen = model.rd_freeze_weights() if hasattr(model, 'rd_freeze_weights') else contextlib.nullcontext()
+            with frozen:
+                for i in range(sde.N - 1):  # the last grid point performs no update (sampling.py:330)
+                    vec_t = torch.ones(shape[0], device=device) * timesteps[i]
+                    if tape is not None:
+                        x = _tape_iteration(pred, corr, x, vec_t, tape, device)
+                    else:
+                        x, _ = corr.update_fn(x, vec_t)
+                        x, _ = pred.update_fn(x, vec_t)
             return x, sde.N * (n_steps + 1)
 
     return pc_sampler

@@ -519,8 +519,9 @@ def ema_update(shadow: List[Tensor], params: List[Tensor], decay: float, num_upd
 
 def gto_halo_decode(samples: np.ndarray, n_variables: int = 67) -> np.ndarray:
     """Latents -> physical units (Benchmark/gto_halo_benchmarking.py:255-328, :335-363), numpy fp32.
-    PARITY UNPINNED: the reference code is the tail of a method whose module imports the CR3BP/SNOPT
-    stack (not importable here), so this restatement is checked by reading, not against its outputs."""
+    Pinned: oracle/make_golden_r2.py imports the benchmark module (absent plotting / optimiser dependencies stubbed),
+    drives the real GTOHaloBenchmarker.generate_samples tail on seeded latents and found this restatement
+    bit-identical (tests/golden/codec.npz, REPORT_r2.txt); tests/test_oracle_golden.py re-checks it."""
     s = np.asarray(samples, dtype=np.float32).reshape(samples.shape[0], -1)[:, :n_variables]
     label = s[:, 0]
     m = s[:, 1:] * np.float32(0.1811) + np.float32(0.4652)  # global mean/std un-normalisation (:266-268)
@@ -546,3 +547,13 @@ def gto_halo_decode(samples: np.ndarray, n_variables: int = 67) -> np.ndarray:
     m[:, -1] = m[:, -1] * np.float32(11 - 5) + np.float32(5)
     halo = label * np.float32(0.095 - 0.008) + np.float32(0.008)
     return np.column_stack((halo, m)).astype(np.float32)
+
+
+def gto_halo_encode(raw: np.ndarray, image_size: int = 9, image_width: Optional[int] = None):
+    """Dataset rows -> latents (datasets.GTOHaloImageDataset.__getitem__, datasets.py:88-98), numpy fp32:
+    zero-pad to H*W, z-score every entry, reshape to [N,1,H,W]; label = un-normalised first value."""
+    W = image_size if image_width is None else image_width
+    raw = np.asarray(raw, dtype=np.float32)
+    padded = np.pad(raw, ((0, 0), (0, image_size * W - raw.shape[1])), "constant")
+    padded = (padded - 0.4652) / 0.1811
+    return padded.reshape(raw.shape[0], 1, image_size, W).astype(np.float32), raw[:, :1].copy()

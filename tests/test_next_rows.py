@@ -265,3 +265,33 @@ def test_codec_vs_oracle(shape):
         codec.gto_halo_decode(torch.rand(4, 1, 8, 8, device="cuda"))
     with pytest.raises(RuntimeError):
         codec.gto_halo_decode(torch.rand(4, 81))
+
+
+@pytest.mark.gpu
+def test_codec_pinned_against_reference_outputs():
+    """tests/golden/codec.npz holds outputs of the reference's OWN code: the tail of GTOHaloBenchmarker.generate_samples
+    (Benchmark/gto_halo_benchmarking.py:255-363) and datasets.GTOHaloImageDataset (datasets.py:82-98), driven by
+    oracle/make_golden_r2.py.  Decode: within 2e-5 (device asin / atan2 vs numpy's); encode: bit-exact."""
+    from helpers import load_golden
+    from rdb200 import codec
+    g = load_golden("codec.npz")
+    got = codec.gto_halo_decode(torch.from_numpy(g["latents"]).cuda()).cpu().numpy()
+    want = g["physical"]
+    d = np.abs(got - want)
+    ang = np.zeros(67, bool)
+    ang[4:64:3] = True
+    ang[5:64:3] = True
+    d[:, ang] = np.minimum(d[:, ang], np.abs(d[:, ang] - 2 * np.pi))
+    assert got.shape == want.shape and float(d.max()) <= 2e-5 * max(1.0, float(np.abs(want).max())), float(d.max())
+    lat, lab = codec.gto_halo_encode(torch.from_numpy(g["raw"]).cuda(), 9)
+    assert torch.equal(lat.cpu(), torch.from_numpy(g["enc_img"])) and torch.equal(lab.cpu(), torch.from_numpy(g["enc_label"]))
+    # encode -> decode round trip of in-range rows returns the physical-unit image of the row (size-independent property)
+    raw = torch.rand(1000, 67, device="cuda")
+    lat, lab = codec.gto_halo_encode(raw, 9)
+    back = codec.gto_halo_decode(lat)
+    want = torch.from_numpy(O.gto_halo_decode(O.gto_halo_encode(raw.cpu().numpy(), 9)[0])).cuda()
+    assert float((back - want).abs().max()) <= 1e-3
+    with pytest.raises(ValueError):
+        codec.GtoHaloConstants(n_variables=66).c_struct()   # 59 control values: not whole triplets
+    with pytest.raises(ValueError):
+        codec.gto_halo_encode(torch.rand(4, 90, device="cuda"), 9)

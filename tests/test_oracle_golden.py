@@ -145,3 +145,34 @@ def test_identities_the_kernels_rely_on_fp64():
         Mc = int(np.ceil(np.sqrt((70 * t + 1) / 4)))
         assert float((O._score_hk_ef(xx, x0, sg ** 2 / 2, Kc) - ef).abs().max()) <= 3e-7 * scale
         assert float((O._score_hk_refl(xx, x0, sg ** 2 / 2, Mc) - im).abs().max()) <= 3e-7 * scale
+
+
+def test_round2_goldens_pin_the_oracle():
+    """Round-2 fixtures (oracle/make_golden_r2.py, outputs of the unmodified reference): the codec restatements are
+    bit-identical, and the oracle's forward reproduces the scale_by_sigma golden (the N=1000 / n_steps_each=2 / C5
+    fixtures were bit-identical at generation time, tests/golden/REPORT_r2.txt; re-running them here would cost minutes
+    of CPU, they are re-checked on the GPU box through the oracle in tests/test_gpu_round2.py)."""
+    g = load_golden("codec.npz")
+    dec = O.gto_halo_decode(g["latents"])
+    assert dec.shape == g["physical"].shape == (64, 67)
+    assert np.array_equal(dec, g["physical"]), float(np.abs(dec - g["physical"]).max())
+    img, lab = O.gto_halo_encode(g["raw"], 9)
+    assert np.array_equal(img, g["enc_img"]) and np.array_equal(lab, g["enc_label"])
+    # padding entries are z-scored too: (0 - mean) / std
+    assert abs(float(img[0, 0, 8, 8]) - (0.0 - 0.4652) / 0.1811) < 1e-6
+    f = load_golden("forward_sbs.npz")
+    cfg = O.NetConfig(image_size=8, attn_resolutions=(8,), scale_by_sigma=True)
+    sd = O.synth_state_dict(cfg, seed=9, out_scale=0.003)
+    with torch.no_grad():
+        y = O.ncsnpp_forward(torch.from_numpy(f["x"]), torch.from_numpy(f["sigma"]), torch.from_numpy(f["labels"]), sd, cfg)
+    assert float((y - torch.from_numpy(f["y"])).abs().max()) <= 2e-5 * float(np.abs(f["y"]).max())
+    s = load_golden("sampler_pc_N40_ns2.npz")
+    N, B = int(s["N"]), int(s["B"])
+    cfg8 = O.NetConfig(image_size=8, attn_resolutions=(8,))
+    sd8 = O.synth_state_dict(cfg8, seed=7)
+    x0, noise = O.make_tape(B, (1, 8, 9), (N - 1) * 3, seed=int(s["tape_seed"]))
+    labels = torch.from_numpy(s["labels"])
+    with torch.no_grad():
+        xo = O.pc_sampler(lambda xx, sg: O.guided_score(xx, sg, labels, float(s["w"]), sd8, cfg8), O.VESchedule(0.01, 5.0, N, 1.0, 1e-5),
+                          O.SamplerConfig(n_steps_each=2), x0, noise)
+    assert float((xo - torch.from_numpy(s["x_final"])).abs().max()) <= 5e-4
