@@ -52,14 +52,34 @@ FLOP_PER_SAMPLE_FORWARD = 207.374848e6   # 8x9, attention at 8 (BASELINE.md sect
 FLOP_PER_SAMPLE = FLOP_PER_SAMPLE_FORWARD * 2 * 2 * ITERS_PER_PASS  # CFG x2, corrector+predictor x2
 METRIC = "GTO-Halo samples/sec (1000-step CFG PC sampler)"
 UNIT = "samples/s"
+# BASELINE.json configs[4] ("C5"): the scaled network; selected with --config c5 (the default line is C3)
+C5 = {"H": 16, "W": 16, "nf": 256, "ch_mult": [1, 2, 2, 2], "attn": [16], "batch_per_gpu": 2048,
+      "flop_per_sample_forward": 12608.866304e6,   # SURVEY.md App. A2 (torch FlopCounter on the reference model)
+      "workload": ("C5: scaled NCSN++ 2D (16x16 reflected latents, nf256, ch_mult [1,2,2,2], 2 res blocks, attention at "
+                   "16x16 = 256 tokens x 256 channels, CFG w=1.5) random-init, reflected PC sampler (Langevin snr 0.01 + "
+                   "Euler-Maruyama), 1000 steps, batch 16384 over 8 GPUs = 2048 per GPU")}
+CONFIG = {"name": "c3", "H": 8, "W": 9}
+
 WORKLOAD = ("C3: GTO-Halo NCSN++ 2D (8x9, nf64, ch_mult [1,2,2], 2 res blocks, attn@8x9, CFG w=1.5) random-init, "
             "reflected PC sampler (Langevin snr 0.01 + Euler-Maruyama), 1000 steps, batch 8192 per GPU")
 
 
+def use_config(name):
+    """Switch the module-level workload description to BASELINE config `name` ("c3" default, "c5")."""
+    global WORKLOAD, FLOP_PER_SAMPLE_FORWARD, FLOP_PER_SAMPLE
+    if name == "c5":
+        CONFIG.update(name="c5", H=C5["H"], W=C5["W"])
+        WORKLOAD = C5["workload"]
+        FLOP_PER_SAMPLE_FORWARD = C5["flop_per_sample_forward"]
+        FLOP_PER_SAMPLE = FLOP_PER_SAMPLE_FORWARD * 2 * 2 * ITERS_PER_PASS
+
+
 def model_config(corrector="langevin"):
+    c5 = CONFIG["name"] == "c5"
     m = types.SimpleNamespace(
-        name="ncsnpp", channels=1, image_size=8, image_width=9, num_classes=1, cond_drop_prob=0.5, conditional=True,
-        init_scale=0.0, ema_rate=0.999, nf=64, ch_mult=[1, 2, 2], num_res_blocks=2, attn_resolutions=[8],
+        name="ncsnpp", channels=1, image_size=CONFIG["H"], image_width=CONFIG["W"], num_classes=1, cond_drop_prob=0.5,
+        conditional=True, init_scale=0.0, ema_rate=0.999, nf=C5["nf"] if c5 else 64, ch_mult=C5["ch_mult"] if c5 else [1, 2, 2],
+        num_res_blocks=2, attn_resolutions=C5["attn"] if c5 else [8],
         resamp_with_conv=True, embedding_type="fourier", fourier_scale=16, skip_rescale=True, nonlinearity="swish",
         fir=False, fir_kernel=[1, 3, 3, 1], dropout=0.2, scale_by_sigma=False)
     s = types.SimpleNamespace(method="pc", predictor="euler_maruyama", corrector=corrector, denoiser="none", snr=0.01,
@@ -135,7 +155,7 @@ def stock_reference_pass(ref, B, N, device, threads=None, weights_seed=0):
     torch.manual_seed(weights_seed)
     model = ref.mutils.create_model(cfg).to(device).eval()   # untouched reference init, like our arm
     sde = ref.sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=N)
-    fn = ref.sampling.get_sampling_fn(cfg, sde, (B, 1, 8, 9), 1e-5, device)
+    fn = ref.sampling.get_sampling_fn(cfg, sde, (B, 1, CONFIG["H"], CONFIG["W"]), 1e-5, device)
     labels = torch.rand((B, 1), generator=torch.Generator().manual_seed(1)).to(device)
     stamps = []
     cuda = torch.device(device).type == "cuda"
@@ -287,6 +307,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8192, help="samples per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c3", "c5"],
+                    help="BASELINE config: c3 = GTO-Halo 8x9 (the metric's configuration, default), c5 = scaled nf256 16x16")
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"], help="network plan precision (default bf16)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: total batch split evenly over the GPUs (BASELINE config C4 = 65536)")
     ap.add_argument("--weight", type=float, default=1.5, help="classifier-free guidance weight (C3 sweep)")
@@ -299,6 +322,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2", action="store_true", help="skip the reflect / score_hk / fused-update HBM microbench")
     args = ap.parse_args()
+    use_config(args.config)
+    if args.config == "c5" and args.batch == 8192:
+        args.batch = C5["batch_per_gpu"]
     _isolate_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -341,8 +367,11 @@ def main():
     sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=SDE_N)
     labels_host = torch.rand((B, 1), generator=torch.Generator().manual_seed(1 + rank)).pin_memory()
     labels = labels_host.to(dev, non_blocking=True)
-    x0 = torch.rand((B, 1, 8, 9), generator=torch.Generator().manual_seed(2 + rank)).to(dev)
-    eng = model.rd_sampler_engine(B, 8, 9, dev, sde, 1e-5, 0.01, 1, cfg=True)
+    H, W = CONFIG["H"], CONFIG["W"]
+    if args.precision:
+        model.rd_set_precision(args.precision)
+    x0 = torch.rand((B, 1, H, W), generator=torch.Generator().manual_seed(2 + rank)).to(dev)
+    eng = model.rd_sampler_engine(B, H, W, dev, sde, 1e-5, 0.01, 1, cfg=True)
     seed = rdd.philox_seed_for_rank(3, rank)
 
     weight = args.weight
@@ -422,12 +451,19 @@ def main():
                 "peak_source": pk["source"] + " (sustained)",
                 "avg_launch_ms": conv_ms / n_conv, "share_of_forward": conv_ms / fwd_ms,
                 "algorithmic_flop_per_launch_avg": conv_flop / n_conv,
-                "sampler_frac": value / world * FLOP_PER_SAMPLE / (pk["bf16_tflops"] * 1e12)}
+                "sampler_frac": value / world * FLOP_PER_SAMPLE / (pk["bf16_tflops"] * 1e12),
+                "forward_ms_by_kind": {k: round(sum(t for t, n in zip(per_op, eng.op_names) if eng.op_kinds[n] == k), 4)
+                                       for k in sorted(set(eng.op_kinds.values()))}}
+        if model.rd_precision == "fp32":
+            # fp32 activations put the network below the ridge point: the bound to read this plan against is
+            # HBM, 1.32 MB of fp32 activation traffic per sample-forward, not the bf16 tensor peak
+            roof["fp32_plan_hbm_bound_samples_per_s"] = pk["hbm_gbs"] * 1e9 / (1.32e6 * 2 * 2 * ITERS_PER_PASS) if args.config == "c3" else None
+            roof["fp32_plan_tensor_work"] = "3 MMAs per k-step (lo*hi + hi*lo + hi*hi): achieved counts algorithmic flops once"
 
     # ---- e2e through the public drop-in API with host buffers
     e2e = None
     if not args.no_e2e:
-        fn = sampling.get_sampling_fn(cfg, sde, (B, 1, 8, 9), 1e-5, dev)
+        fn = sampling.get_sampling_fn(cfg, sde, (B, 1, H, W), 1e-5, dev)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -444,7 +480,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
         assert bool(((host >= 0) & (host <= 1)).all())
-        e2e = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(B * 4 + B * 72 * 4),
+        e2e = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(B * 4 + B * H * W * 4),
                "d2h_bytes_per_step": int(host.numel() * 4 // (world if world > 1 else 1)), "seconds_per_pass": dt,
                "call": "sampling.get_sampling_fn(config, sde, shape, eps, device)(model, weight=1.5, class_labels=...)"}
 
@@ -456,7 +492,7 @@ def main():
     # ---- the HBM-bound kernels of the path (BASELINE config C2 shape, [2^20,1,8,9]): achieved GB/s of algorithmic
     # bytes against the measured copy bandwidth, timed live with CUDA events (tools/bench_c2.py)
     hbm = None
-    if not args.no_c2:
+    if not args.no_c2 and args.config == "c3":
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_c2
@@ -476,7 +512,7 @@ def main():
             hbm = [{"error": repr(e)}]
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and args.config == "c3":
         r = cpu_reference_c1(20, 5, passes=1)   # bounded sample: one C1 pass (batch 128, 100 steps) on the host cores
         cpu = {"value": r["B"] / (ITERS_PER_PASS * r["ms"] / 1e3), "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                "sample": r["sample"], "batch": r["B"], "c1_pass_seconds": r["c1_pass_seconds"]}
@@ -493,7 +529,8 @@ def main():
         config["guidance"] = ("per-sample w = %g*U[0,1]" % args.weight) if args.per_sample_weight else ("w = %g" % args.weight)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": config,
+            "dtype": "bf16" if model.rd_precision == "bf16" else "f32 (split-bf16 tensor-core operands)", "data": "synthetic",
+            "config": config,
             "run": {"noise": "in-kernel Philox", "cuda_graph": True, "all_gather_ms": ag_ms, "all_samples_inside_cube": inside},
             "clocks": clk, "roofline": roof, "hbm_kernels": {"shape": "[2^20,1,8,9] fp32 (C2)", "peak_GBps": pk["hbm_gbs"],
                                                               "peak_source": pk["source"], "rows": hbm},

@@ -59,6 +59,14 @@ int rd_inside_f32(const float* x, uint8_t* ok, size_t B, size_t D, void* stream)
 int rd_score_hk_f32(const float* x, const float* x_orig, const float* sigma, float sigma_scalar, float* out,
                     size_t B, size_t D, int efs, int refls, float min_cutoff, void* stream);
 
+/* Same function through the streaming path: a pre-pass classifies the samples into `workspace` (caller-owned device
+ * memory, >= rd_score_hk_workspace_bytes(B), 16-byte aligned), then one barrier-free grid-stride kernel evaluates the
+ * elements.  workspace == NULL (or too small) falls back to the single-kernel path above. */
+size_t rd_score_hk_workspace_bytes(size_t B);
+int rd_score_hk_ws_f32(const float* x, const float* x_orig, const float* sigma, float sigma_scalar, float* out,
+                       size_t B, size_t D, int efs, int refls, float min_cutoff, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* ---------------------------------------------------------------- noise */
 /* out[0..n) = the N(0,1) stream the fused step kernels draw for (seed, draw): element i is lane i%4 of Philox quad i/4
  * (any n; quads are indexed over the flat tensor). */
@@ -252,6 +260,16 @@ typedef struct rd_op {
   } u;
 } rd_op;
 
+/* Unit entry points -- one reference layer per call, on caller-owned NHWC buffers:
+ *   rd_resblock   ResnetBlockDDPMpp.forward (layerspp.py:198-214): [temb: Dense_0(act(temb)) rows] -> [shortcut: NIN_0] ->
+ *                 conv0 (GN0 + SiLU + Conv_0 + temb rows) -> conv1 (GN1 + SiLU + Conv_1 + skip, * out_scale); temb /
+ *                 shortcut may be NULL; shortcut / conv0 / conv1 are arrays of n_slices channel-slice launches each
+ *                 (1 for C_out <= 128, see rd_op_conv.out_stride)
+ *   rd_attn_block AttnBlockpp.forward (layerspp.py:80-96), the fused kernel (C = 64, T <= 128, bf16 plan) */
+int rd_resblock(const rd_op_temb* temb, const rd_op_conv* shortcut, const rd_op_conv* conv0, const rd_op_conv* conv1, int n_slices,
+                void* stream);
+int rd_attn_block(const rd_op_attn_block* op, void* stream);
+
 typedef struct rd_plan rd_plan;
 int rd_plan_create(rd_plan** out);
 int rd_plan_add(rd_plan* p, const rd_op* op);
@@ -262,6 +280,10 @@ int rd_plan_run_range(rd_plan* p, int first, int count, void* stream);
 int rd_plan_destroy(rd_plan* p);
 /* shared-memory bytes / CTAs a conv op will launch with (planner feedback, also validates the op) */
 int rd_conv_launch_info(const rd_op_conv* op, int* smem_bytes, int* grid, int* rows_alloc);
+/* the tile geometry picked for a conv op: geom[12] = {samples per group, 128-row tiles, staged rows, groups, operand stages,
+ * filter resident?, filter ring slabs, accumulator buffers, register-cached transform slots (0 = streaming), shared-memory
+ * bytes, grid, TMEM columns} (profiling / planner feedback) */
+int rd_conv_geometry(const rd_op_conv* op, int* geom);
 
 /* ---------------------------------------------------------------- parameter change detection */
 /* 64-bit content checksum of a set of fp32 device tensors (value AND position of every element enter the sum), so the

@@ -321,17 +321,17 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
     }
     team_sync();
     // ---- per-channel affine of the group statistics: thread c sums its group's channels over the warps' partials
-    if (tid < C) {
-      const int c0 = (tid / cpg) * cpg;
+    for (int ch = tid; ch < C; ch += nthr) {  // (a team of one warp -- T <= 16 -- covers the 64 channels in two rounds)
+      const int c0 = (ch / cpg) * cpg;
       float a1 = 0.0f, a2 = 0.0f;
       for (int w = 0; w < T16; ++w)
         for (int c = c0; c < c0 + cpg; ++c) { a1 += s_pt[w * 2 * C + c]; a2 += s_pt[w * 2 * C + C + c]; }
       const float inv = 1.0f / static_cast<float>(cpg * T);
       const float mean = a1 * inv;
       const float var = fmaxf(a2 * inv - mean * mean, 0.0f);
-      const float ca = s_ga[tid] / sqrtf(var + eps);
-      s_cf[tid] = ca;
-      s_cf[C + tid] = fmaf(-mean, ca, s_be[tid]);
+      const float ca = s_ga[ch] / sqrtf(var + eps);
+      s_cf[ch] = ca;
+      s_cf[C + ch] = fmaf(-mean, ca, s_be[ch]);
     }
     team_sync();
     {

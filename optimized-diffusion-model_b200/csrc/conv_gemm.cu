@@ -38,6 +38,11 @@
 #include "rd_common.h"
 #include "rd_ptx.cuh"
 
+// Role-cost ablations for MEASUREMENT BUILDS ONLY (rdb200/build.py `defines`, tools/run_ablate.sh): each macro removes one
+// role's work while keeping every barrier hand-off, so the per-launch times show which role a layer waits for.  The
+// product library defines none of them; results of an ablated build are garbage.
+//   RD_ABL_NO_MMA    no tcgen05.mma issued          RD_ABL_NO_EPI   epilogue does no TMEM load / math / global access
+//   RD_ABL_NO_XFORM  transform does no global load / math / st.shared   RD_ABL_NO_WSTREAM  streamed filters not copied
 namespace rd {
 
 constexpr int CONV_THREADS = 512;
@@ -167,6 +172,9 @@ __device__ __forceinline__ void issue_tap(uint32_t acc, uint32_t N, uint32_t a_l
                                           uint32_t a_half, uint32_t w_half) {
   // one k-step of one tile: a single MMA, or (x3) the three split-bf16 terms, small ones first
   auto kstep = [&](uint32_t d, uint32_t a, uint32_t w, uint32_t acc_flag) {
+#ifdef RD_ABL_NO_MMA
+    return;
+#endif
     if (X3) {
       umma_bf16_ss(d, desc_hi | (a + a_half), desc_hi | w, idesc, acc_flag);  // lo * hi
       umma_bf16_ss(d, desc_hi | a, desc_hi | (w + w_half), idesc, 1u);        // hi * lo
@@ -476,8 +484,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       int ws = 0, e_par = 1, slab = 0;
       for (int it = 0; it < total; ++it) {
         if (it >= w_stages) mbar_wait(&bar_w_empty[ws], e_par);
+#ifdef RD_ABL_NO_WSTREAM
+        mbar_arrive(&bar_w_full[ws]);
+#else
         mbar_arrive_expect_tx(&bar_w_full[ws], p.w_slab_bytes);
         bulk_g2s(Ws + ws * p.w_slab_bytes, wg + static_cast<size_t>(slab) * p.w_slab_bytes, p.w_slab_bytes, &bar_w_full[ws]);
+#endif
         if (++ws == w_stages) { ws = 0; e_par ^= 1; }   // first wait on a slot (round 1) uses parity 0
         if (++slab == n_slabs) slab = 0;                  // natural (chunk, tap) order, restarted for every group
       }
@@ -531,6 +543,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       for (int tile = 0; tile < n_tiles; ++tile) {
         const int row = tile * 128 + et;
         const int orow = t_orow[row];
+#ifdef RD_ABL_NO_EPI
+        continue;
+#endif
         const bool valid = orow >= 0 && orow < valid_limit;
         const float* btr = bt + t_os[row] * N;
         if constexpr (X3) {
@@ -670,7 +685,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       uint4 raw[RCN], nxt[PREFETCH ? RCN : 1];
       auto load_group = [&](uint4* dst, int li) {
         const int g = blockIdx.x + li * gridDim.x;
+#ifdef RD_ABL_NO_XFORM
+        const bool active = false;
+#else
         const bool active = owner && s < min(p.S, p.B2 - g * p.S);
+#endif
         const __nv_bfloat16* gbase = reinterpret_cast<const __nv_bfloat16*>(which ? src1 : src0) +
                                      static_cast<size_t>(g) * (which ? gstride1 : gstride0) + coff;
 #pragma unroll
@@ -683,7 +702,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
         const int S_act = max(0, min(p.S, p.B2 - g * p.S));
+#ifdef RD_ABL_NO_XFORM
+        const bool active = false;
+#else
         const bool active = owner && s < S_act;
+#endif
         if (!PREFETCH && li > 0) load_group(raw, li);
         float sum[8], sq[8];
 #pragma unroll
@@ -744,7 +767,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const act_t* base = (which ? src1 + static_cast<size_t>(g) * gstride1 - p.C[0]
                                    : src0 + static_cast<size_t>(g) * gstride0) + chunk * 64;
         const int* toff = t_off + (which ? p.S * P : 0);
+#ifdef RD_ABL_NO_XFORM
+        const int items = 0;
+#else
         const int items = S_act * P * 8;
+#endif
         for (int item = xt; item < items; item += XFORM_THREADS) {
           const int sp = item >> 3, kcl = item & 7;
           cp_async16(a4 + kcl * p.R + t_row[sp], base + toff[sp] + kcl * 8);
@@ -768,7 +795,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       };
       for (int li = 0; li < my_groups; ++li) {
         const int g = blockIdx.x + li * gridDim.x;
+#ifdef RD_ABL_NO_XFORM
+        const int S_act = 0;
+#else
         const int S_act = max(0, min(p.S, p.B2 - g * p.S));
+#endif
         const act_t* gb0 = src0 + static_cast<size_t>(g) * gstride0;
         const act_t* gb1 = p.nsrc > 1 ? src1 + static_cast<size_t>(g) * gstride1 : gb0;
         if (GNM != GNM_NONE) {
@@ -1095,5 +1126,18 @@ extern "C" int rd_conv_launch_info(const rd_op_conv* op, int* smem_bytes, int* g
   if (smem_bytes) *smem_bytes = smem;
   if (grid) *grid = g;
   if (rows_alloc) *rows_alloc = p.R;
+  return RD_OK;
+}
+
+// planner / profiling feedback: the tile geometry the library picks for `op`
+//   geom = {S, n_tiles, R, n_groups, a_stages, w_resident, w_stages, acc_bufs, xmode, smem_bytes, grid, tmem_cols}
+extern "C" int rd_conv_geometry(const rd_op_conv* op, int* geom) {
+  RD_REQUIRE(op && geom, "rd_conv_geometry: null argument");
+  rd::ConvParams p;
+  int smem = 0, g = 0;
+  int rc = rd::conv_make_params(*op, p, smem, g);
+  if (rc != RD_OK) return rc;
+  const int v[12] = {p.S, p.n_tiles, p.R, p.n_groups, p.a_stages, p.w_resident, p.w_stages, p.acc_bufs, p.xmode, smem, g, p.tmem_cols};
+  for (int i = 0; i < 12; ++i) geom[i] = v[i];
   return RD_OK;
 }

@@ -90,12 +90,15 @@ constexpr int HK_MAX_EFS = 64;  // table capacity per sample
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr float PI2_F = 9.869604401089358f;  // python float pi**2 -> fp32 scalar
 constexpr float HK_T_IMAGES = 0.214f;        // above this the eigen-series (<= 5 modes) is the cheaper form
+// Below this t the far image -2 - x (|d| >= 2) is under e^-17.5 of the sum: den >= exp(-1/4t) (the image x itself has
+// |d| <= 1) against exp(-4/4t).  It covers every t for which one image pair per side suffices (Mc == 1 <=> t <= 0.04286).
+constexpr float HK_T_FIVE = 0.0429f;
 
 struct HkSampleTab {
-  float c_exp[HK_SPB];   // images: -log2(e) / (4t)
-  float scale[HK_SPB];   // images: -2 / (4t)
+  float sc[HK_SPB];      // images: sqrt(log2(e) / (4t)); distances are carried in these units so that e = ex2(-d'^2)
+  float scale[HK_SPB];   // images: (-2 / (4t)) / sc
   float eps[HK_SPB];     // denominator epsilon in this form's units
-  int count[HK_SPB];     // images: M (|m| <= M), modes: K
+  int count[HK_SPB];     // images: M (|m| <= M; 0 = the five-image form), modes: K
   int modes[HK_SPB];     // 1: eigen-series, 0: images
   int order[HK_SPB];     // order[slot] = sample visited at that slot
 };
@@ -105,16 +108,43 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
+// Eigen-series (cube.py:92-107) for t > HK_T_IMAGES: at most five modes survive, harmonics by the rotation recurrence.
+// sin / cos(pi x) come from the special-function unit: x, x0 lie in [0,1], so the argument is inside [0, pi] where
+// sin.approx / cos.approx are accurate to 2^-21 absolute -- 4e-7 of a score whose scale is set by the same e_1.
 __device__ __forceinline__ float hk_modes(float x, float x0, const float2* __restrict__ e, int K, float eps) {
+  const float s1 = __sinf(PI_F * x), c1 = __cosf(PI_F * x);
+  const float s01 = __sinf(PI_F * x0), c01 = __cosf(PI_F * x0);
+  float s = s1, c = c1, s0 = s01, c0 = c01;
+  float2 ek = e[0];                          // (exp(-t k^2 pi^2), k * exp(-t k^2 pi^2))
+  float den = ek.x * (c * c0), num = ek.y * (s * c0);
+  for (int k = 1; k < K; ++k) {
+    const float cn = fmaf(c, c1, -s * s1), sn = fmaf(s, c1, c * s1);
+    const float c0n = fmaf(c0, c01, -s0 * s01), s0n = fmaf(s0, c01, c0 * s01);
+    c = cn; s = sn; c0 = c0n; s0 = s0n;
+    ek = e[k];
+    den = fmaf(ek.x, c * c0, den);           // cos(k pi x) cos(k pi x0)
+    num = fmaf(ek.y, s * c0, num);           // k sin(k pi x) cos(k pi x0)
+  }
+  return (-2.0f * PI_F * num) * rcp_approx(fmaf(2.0f, den, 1.0f) + eps);
+}
+
+// Accurate-trig variant for arguments outside [0,1] (score_hk is only specified on the cube, but the reference
+// evaluates whatever it is given).
+__device__ __forceinline__ float hk_modes_any(float x, float x0, const float2* __restrict__ e, int K, float eps) {
   float s1, c1, s01, c01;
-  sincospif(x, &s1, &c1);     // sin(pi x), cos(pi x)
+  sincospif(x, &s1, &c1);
   sincospif(x0, &s01, &c01);
   float s = s1, c = c1, s0 = s01, c0 = c01, num = 0.0f, den = 0.0f;
   for (int k = 0; k < K; ++k) {
-    const float2 ek = e[k];                  // (exp(-t k^2 pi^2), k * exp(-t k^2 pi^2))
-    den = fmaf(ek.x, c * c0, den);           // cos(k pi x) cos(k pi x0)
-    num = fmaf(ek.y, s * c0, num);           // k sin(k pi x) cos(k pi x0)
+    const float2 ek = e[k];
+    den = fmaf(ek.x, c * c0, den);
+    num = fmaf(ek.y, s * c0, num);
     const float cn = fmaf(c, c1, -s * s1), sn = fmaf(s, c1, c * s1);
     const float c0n = fmaf(c0, c01, -s0 * s01), s0n = fmaf(s0, c01, c0 * s01);
     c = cn; s = sn; c0 = c0n; s0 = s0n;
@@ -122,30 +152,37 @@ __device__ __forceinline__ float hk_modes(float x, float x0, const float2* __res
   return __fdividef(-2.0f * PI_F * num, fmaf(2.0f, den, 1.0f) + eps);
 }
 
-// M is a compile-time constant for the two cases that cover every converged sum below HK_T_IMAGES (6 and 10
-// images): fully unrolled, image offsets folded into immediates, two independent accumulator chains.
-template <int MC>
-__device__ __forceinline__ float hk_images_fixed(float x, float x0, float c_exp, float scale, float eps) {
+// Method of images (cube.py:129-146).  Distances are formed in x units exactly as the reference forms them --
+// (2m + x) - x0 and (2m - x) - x0, so the near-wall images whose distance is a small difference of O(1) numbers keep
+// it exact -- and only then scaled by sc = sqrt(log2(e) / 4t): the Gaussian of an image is ex2(-d'^2), and
+// sum(sign d e) / sum(e) picks up the common factor (-2/4t)/sc once at the end.
+//   FIVE: images x-2, x, x+2, -x, 2-x (the converged sum for t <= HK_T_FIVE);  MC: |m| <= MC on both families.
+template <int MC, bool FIVE>
+__device__ __forceinline__ float hk_images_fixed(float x, float x0, float sc, float scale, float eps) {
   float numa = 0.0f, numb = 0.0f, dena = 0.0f, denb = 0.0f;
 #pragma unroll
   for (int m = -MC; m <= MC; ++m) {
     const float r = static_cast<float>(2 * m);
-    const float da = (r + x) - x0, db = (r - x) - x0;
-    const float ea = ex2_approx(da * da * c_exp), eb = ex2_approx(db * db * c_exp);
+    const float da = ((r + x) - x0) * sc;
+    const float ea = ex2_approx(-(da * da));
     numa = fmaf(da, ea, numa);
-    numb = fmaf(db, eb, numb);
     dena += ea;
-    denb += eb;
+    if (!(FIVE && m == -MC)) {
+      const float db = ((r - x) - x0) * sc;
+      const float eb = ex2_approx(-(db * db));
+      numb = fmaf(db, eb, numb);
+      denb += eb;
+    }
   }
-  return __fdividef(scale * (numa - numb), (dena + denb) + eps);
+  return (scale * (numa - numb)) * rcp_approx((dena + denb) + eps);
 }
 
-__device__ __forceinline__ float hk_images(float x, float x0, float c_exp, float scale, int M, float eps) {
+__device__ __forceinline__ float hk_images(float x, float x0, float sc, float scale, int M, float eps) {
   float num = 0.0f, den = 0.0f;
   for (int m = -M; m <= M; ++m) {
     const float r = static_cast<float>(2 * m);
-    const float da = (r + x) - x0, db = (r - x) - x0;   // images 2m + x (sign +) and 2m - x (sign -)
-    const float ea = ex2_approx(da * da * c_exp), eb = ex2_approx(db * db * c_exp);
+    const float da = ((r + x) - x0) * sc, db = ((r - x) - x0) * sc;   // images 2m + x (sign +) and 2m - x (sign -)
+    const float ea = ex2_approx(-(da * da)), eb = ex2_approx(-(db * db));
     num = fmaf(da, ea, num);
     num = fmaf(-db, eb, num);
     den += ea;
@@ -154,8 +191,42 @@ __device__ __forceinline__ float hk_images(float x, float x0, float c_exp, float
   return __fdividef(scale * num, den + eps);
 }
 
+// Which form / how many terms a sample needs (shared by the single-kernel path and the streaming path's pre-pass).
+//   form 0: images |m| <= count   1: eigen-series, count modes   2: empty series (efs == 0)   3: the five-image form
+enum { HK_IMAGES = 0, HK_MODES = 1, HK_EMPTY = 2, HK_FIVE = 3 };
+struct HkClass {
+  int form, count;
+  float t, sc, scale, eps;
+};
+__device__ __forceinline__ HkClass hk_classify(float sg, int efs, int refls, float min_cutoff) {
+  HkClass c;
+  const float t = __fdiv_rn(__fmul_rn(sg, sg), 2.0f);  // sigma ** 2 / 2
+  const int Kc = static_cast<int>(fminf(ceilf(sqrtf(17.5f / (PI2_F * t))) + 1.0f, 1.0e6f));
+  const int Mc = static_cast<int>(fminf(ceilf(sqrtf(0.25f * fmaf(70.0f, t, 1.0f))), 1.0e6f));
+  c.t = t;
+  c.eps = 1e-12f;
+  if (t > min_cutoff) {            // the reference's ef_cond (cube.py:176)
+    if (efs >= Kc && t <= HK_T_IMAGES) {
+      c.form = HK_IMAGES; c.count = Mc;       // converged series == converged image sum
+      c.eps = 1e-12f * sqrtf(4.0f * PI_F * t);
+    } else if (efs == 0) {
+      c.form = HK_EMPTY; c.count = 0;          // num = 0, den = 1
+    } else {
+      c.form = HK_MODES; c.count = min(efs, min(Kc, HK_MAX_EFS));
+    }
+  } else {
+    c.form = HK_IMAGES; c.count = min(refls, Mc);
+  }
+  if (c.form == HK_IMAGES && c.count == 1 && Mc == 1 && t <= HK_T_FIVE) c.form = HK_FIVE;
+  // (t != t: NaN sigma) -> NaN out through the image form
+  c.sc = sqrtf(1.4426950408889634f / (4.0f * t));
+  c.scale = (-2.0f / (4.0f * t)) / c.sc;
+  return c;
+}
+
+// VEC consecutive elements of one sample per thread and pass (8: 256-bit accesses, two independent chains per form).
 template <int VEC>
-__global__ void __launch_bounds__(256) score_hk_kernel(const float* __restrict__ x, const float* __restrict__ x0,
+__global__ void __launch_bounds__(288) score_hk_kernel(const float* __restrict__ x, const float* __restrict__ x0,
                                                        const float* __restrict__ sigma, float sigma_scalar,
                                                        float* __restrict__ out, size_t B, int D, int efs, int refls,
                                                        float min_cutoff) {
@@ -168,33 +239,17 @@ __global__ void __launch_bounds__(256) score_hk_kernel(const float* __restrict__
     const int i = threadIdx.x;
     int key = 0x7fffffff;
     if (i < ns) {
-      const float sg = sigma ? sigma[s0 + i] : sigma_scalar;
-      const float t = __fdiv_rn(__fmul_rn(sg, sg), 2.0f);  // sigma ** 2 / 2
-      const int Kc = static_cast<int>(fminf(ceilf(sqrtf(17.5f / (PI2_F * t))) + 1.0f, 1.0e6f));
-      const int Mc = static_cast<int>(fminf(ceilf(sqrtf(0.25f * fmaf(70.0f, t, 1.0f))), 1.0e6f));
-      int modes, count;
-      float eps = 1e-12f;
-      if (t > min_cutoff) {            // the reference's ef_cond (cube.py:176)
-        if (efs >= Kc && t <= HK_T_IMAGES) {
-          modes = 0; count = Mc;       // converged series == converged image sum
-          eps = 1e-12f * sqrtf(4.0f * PI_F * t);
-        } else {
-          modes = 1; count = min(efs, min(Kc, HK_MAX_EFS));
-        }
-      } else {
-        modes = 0; count = min(refls, Mc);
-      }
-      // (t != t: NaN sigma) -> NaN out through the image form
-      tab.c_exp[i] = -1.4426950408889634f / (4.0f * t);
-      tab.scale[i] = -2.0f / (4.0f * t);
-      tab.eps[i] = eps;
-      tab.count[i] = count;
-      tab.modes[i] = modes;
-      key = (modes << 20) | min(count, (1 << 20) - 1);
-      if (modes) {
-        for (int k = 1; k <= count; ++k) {
+      const HkClass c = hk_classify(sigma ? sigma[s0 + i] : sigma_scalar, efs, refls, min_cutoff);
+      tab.sc[i] = c.sc;
+      tab.scale[i] = c.scale;
+      tab.eps[i] = c.eps;
+      tab.count[i] = c.count;
+      tab.modes[i] = c.form;
+      key = (c.form << 20) | min(c.count, (1 << 20) - 1);
+      if (c.form == HK_MODES) {
+        for (int k = 1; k <= c.count; ++k) {
           const float kf = static_cast<float>(k);
-          const float ev = expf(__fmul_rn(__fmul_rn(-t, __fmul_rn(kf, kf)), PI2_F));  // exp(-t k^2 pi^2) (cube.py:103-104)
+          const float ev = expf(__fmul_rn(__fmul_rn(-c.t, __fmul_rn(kf, kf)), PI2_F));  // exp(-t k^2 pi^2) (cube.py:103-104)
           e_tab[i][k - 1] = make_float2(ev, ev * kf);
         }
       }
@@ -213,41 +268,241 @@ __global__ void __launch_bounds__(256) score_hk_kernel(const float* __restrict__
   const size_t base = s0 * D;
   const int nelem = ns * D;
   for (int e = threadIdx.x * VEC; e < nelem; e += blockDim.x * VEC) {
-    const int slot = e / D;  // VEC==4 requires D % 4 == 0 so a vector never straddles samples
+    const int slot = e / D;  // VEC > 1 requires D % VEC == 0 so a vector never straddles samples
     const int s = tab.order[slot];
     const size_t off = base + static_cast<size_t>(s) * D + (e - slot * D);
     float xv[VEC], x0v[VEC], r[VEC];
-    if (VEC == 4) {
-      float4 a = ld_stream4(x + off), b = ld_stream4(x0 + off);
-      xv[0] = a.x; xv[1 % VEC] = a.y; xv[2 % VEC] = a.z; xv[3 % VEC] = a.w;
-      x0v[0] = b.x; x0v[1 % VEC] = b.y; x0v[2 % VEC] = b.z; x0v[3 % VEC] = b.w;
-    } else {
+    if (VEC == 1) {
       xv[0] = x[off];
       x0v[0] = x0[off];
-    }
-    const int cnt = tab.count[s];
-    const float eps = tab.eps[s];
-    if (tab.modes[s]) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) r[v] = hk_modes(xv[v], x0v[v], e_tab[s], cnt, eps);
     } else {
-      const float ce = tab.c_exp[s], sc = tab.scale[s];
-      if (cnt == 1) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<1>(xv[v], x0v[v], ce, sc, eps);
-      } else if (cnt == 2) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<2>(xv[v], x0v[v], ce, sc, eps);
-      } else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) r[v] = hk_images(xv[v], x0v[v], ce, sc, cnt, eps);
+      for (int h = 0; h < VEC / 4; ++h) {
+        const float4 a = ld_stream4(x + off + 4 * h), b = ld_stream4(x0 + off + 4 * h);
+        xv[(4 * h) % VEC] = a.x; xv[(4 * h + 1) % VEC] = a.y; xv[(4 * h + 2) % VEC] = a.z; xv[(4 * h + 3) % VEC] = a.w;
+        x0v[(4 * h) % VEC] = b.x; x0v[(4 * h + 1) % VEC] = b.y; x0v[(4 * h + 2) % VEC] = b.z; x0v[(4 * h + 3) % VEC] = b.w;
       }
     }
-    if (VEC == 4) {
-      st_stream4(out + off, make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]));
+    const int cnt = tab.count[s], form = tab.modes[s];
+    const float eps = tab.eps[s];
+    if (form == HK_MODES) {
+      bool in_cube = true;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) in_cube = in_cube && xv[v] >= 0.0f && xv[v] <= 1.0f && x0v[v] >= 0.0f && x0v[v] <= 1.0f;
+      if (in_cube) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = hk_modes(xv[v], x0v[v], e_tab[s], cnt, eps);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = hk_modes_any(xv[v], x0v[v], e_tab[s], cnt, eps);
+      }
+    } else if (form == HK_EMPTY) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) r[v] = -0.0f;  // -2 pi * (empty sum) / (1 + eps), whatever x is
     } else {
-      out[off] = r[0];
+      const float sc = tab.sc[s], scl = tab.scale[s];
+      if (form == HK_FIVE) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<1, true>(xv[v], x0v[v], sc, scl, eps);
+      } else if (cnt == 1) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<1, false>(xv[v], x0v[v], sc, scl, eps);
+      } else if (cnt == 2) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<2, false>(xv[v], x0v[v], sc, scl, eps);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) r[v] = hk_images(xv[v], x0v[v], sc, scl, cnt, eps);
+      }
     }
+    if (VEC == 1) {
+      out[off] = r[0];
+    } else {
+#pragma unroll
+      for (int h = 0; h < VEC / 4; ++h)
+        st_stream4(out + off + 4 * h, make_float4(r[(4 * h) % VEC], r[(4 * h + 1) % VEC], r[(4 * h + 2) % VEC], r[(4 * h + 3) % VEC]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming path of cube.score_hk (used whenever the caller provides a workspace): the per-sample classification is a
+// pre-pass over sigma alone (17 bytes per sample: a 16-byte record and the sample's slot in its 256-sample tile, sorted
+// by form), and the element kernel is a pure grid-stride stream -- no shared memory, no barrier, the next vector's
+// loads in flight while the current one is evaluated.
+struct HkRec {
+  float a;    // images: sc                 modes: e1 = exp(-t pi^2) (e_k = e1^(k^2))    slow modes: t
+  float b;    // images: (-2/4t)/sc
+  float eps;
+  int fc;     // form | count << 8 ;  forms as HK_*, plus HK_MODES_SLOW for series longer than 4 modes
+};
+enum { HK_MODES_SLOW = 4 };
+
+constexpr int HK_TILE = 256;   // samples per sorting tile of the streaming path (slot index fits one byte)
+constexpr int HK_BINS = 5 * (HK_MAX_EFS + 1);
+
+// One block = one tile of HK_TILE samples: classify, then counting-sort the tile by (form, term count) so that the
+// threads of a warp of the element kernel evaluate the same series for the same number of terms even when sigma
+// differs from sample to sample (order within a key is arbitrary and irrelevant).
+__global__ void __launch_bounds__(HK_TILE) hk_prepare_kernel(const float* __restrict__ sigma, float sigma_scalar, size_t B, int efs,
+                                                             int refls, float min_cutoff, HkRec* __restrict__ rec,
+                                                             unsigned char* __restrict__ order) {
+  __shared__ int hist[HK_BINS];
+  const size_t base = static_cast<size_t>(blockIdx.x) * HK_TILE;
+  const size_t i = base + threadIdx.x;
+  for (int k = threadIdx.x; k < HK_BINS; k += HK_TILE) hist[k] = 0;
+  __syncthreads();
+  int bin = -1, pos = 0;
+  if (i < B) {
+    const HkClass c = hk_classify(sigma ? sigma[i] : sigma_scalar, efs, refls, min_cutoff);
+    HkRec r;
+    int form = c.form;
+    r.a = c.sc; r.b = c.scale; r.eps = c.eps;
+    if (form == HK_MODES) {
+      if (c.count <= 4) r.a = expf(__fmul_rn(-c.t, PI2_F));
+      else { form = HK_MODES_SLOW; r.a = c.t; }
+    }
+    r.fc = form | (c.count << 8);
+    rec[i] = r;
+    bin = form * (HK_MAX_EFS + 1) + min(c.count, HK_MAX_EFS);
+  }
+  {
+    // warp-aggregated histogram insert: with one sigma for the whole batch every sample lands in the same bin, and 256
+    // serialised shared-memory atomics on one address cost more than the classification itself
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int start = 0;
+    if (lane == leader && bin >= 0) start = atomicAdd(&hist[bin], __popc(peers));
+    start = __shfl_sync(0xffffffffu, start, leader);
+    pos = start + __popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // exclusive prefix over the (few hundred, mostly empty) bins
+    int run = 0;
+    for (int k = 0; k < HK_BINS; ++k) { const int n = hist[k]; hist[k] = run; run += n; }
+  }
+  __syncthreads();
+  if (i < B) order[base + hist[bin] + pos] = static_cast<unsigned char>(threadIdx.x);
+}
+
+// Eigen-series with at most four modes, e_k = e1^(k^2) by repeated squaring (the relative error of the higher powers,
+// ~k^2 2^-24, sits on terms that are already e1^3 .. e1^15 times smaller than the first).
+__device__ __forceinline__ float hk_modes4(float x, float x0, float e1, int K, float eps) {
+  // sin / cos(pi x) on the special-function unit, accurate to 2^-21 absolute for arguments in [-pi, pi]: x is first
+  // reduced to [-1, 1] by its exact period 2 (a no-op on the cube, where score_hk is specified)
+  x = fmaf(-2.0f, rintf(0.5f * x), x);
+  x0 = fmaf(-2.0f, rintf(0.5f * x0), x0);
+  const float s1 = __sinf(PI_F * x), c1 = __cosf(PI_F * x), s01 = __sinf(PI_F * x0), c01 = __cosf(PI_F * x0);
+  const float e1_2 = e1 * e1, e2 = e1_2 * e1_2, e1_8 = e2 * e2;
+  const float ek[4] = {e1, e2, e1_8 * e1, e1_8 * e1_8};
+  float s = s1, c = c1, s0 = s01, c0 = c01;
+  float den = ek[0] * (c * c0), num = ek[0] * (s * c0);
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    if (k < K) {
+      const float cn = fmaf(c, c1, -s * s1), sn = fmaf(s, c1, c * s1);
+      const float c0n = fmaf(c0, c01, -s0 * s01), s0n = fmaf(s0, c01, c0 * s01);
+      c = cn; s = sn; c0 = c0n; s0 = s0n;
+      den = fmaf(ek[k], c * c0, den);
+      num = fmaf(ek[k] * static_cast<float>(k + 1), s * c0, num);
+    }
+  }
+  return (-2.0f * PI_F * num) * rcp_approx(fmaf(2.0f, den, 1.0f) + eps);
+}
+
+__device__ __forceinline__ float hk_modes_slow(float x, float x0, float t, int K, float eps) {
+  float s1, c1, s01, c01;
+  sincospif(x, &s1, &c1);
+  sincospif(x0, &s01, &c01);
+  float s = s1, c = c1, s0 = s01, c0 = c01, num = 0.0f, den = 0.0f;
+  for (int k = 1; k <= K; ++k) {
+    const float kf = static_cast<float>(k);
+    const float ev = expf(__fmul_rn(__fmul_rn(-t, __fmul_rn(kf, kf)), PI2_F));
+    den = fmaf(ev, c * c0, den);
+    num = fmaf(ev * kf, s * c0, num);
+    const float cn = fmaf(c, c1, -s * s1), sn = fmaf(s, c1, c * s1);
+    const float c0n = fmaf(c0, c01, -s0 * s01), s0n = fmaf(s0, c01, c0 * s01);
+    c = cn; s = sn; c0 = c0n; s0 = s0n;
+  }
+  return __fdividef(-2.0f * PI_F * num, fmaf(2.0f, den, 1.0f) + eps);
+}
+
+template <int VEC>
+__device__ __forceinline__ void hk_eval(const float (&xv)[VEC], const float (&x0v)[VEC], const HkRec rc, float (&r)[VEC]) {
+  const int form = rc.fc & 0xff, cnt = rc.fc >> 8;
+  if (form == HK_FIVE) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<1, true>(xv[v], x0v[v], rc.a, rc.b, rc.eps);
+  } else if (form == HK_IMAGES) {
+    if (cnt == 1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<1, false>(xv[v], x0v[v], rc.a, rc.b, rc.eps);
+    } else if (cnt == 2) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) r[v] = hk_images_fixed<2, false>(xv[v], x0v[v], rc.a, rc.b, rc.eps);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) r[v] = hk_images(xv[v], x0v[v], rc.a, rc.b, cnt, rc.eps);
+    }
+  } else if (form == HK_MODES) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r[v] = hk_modes4(xv[v], x0v[v], rc.a, cnt, rc.eps);
+  } else if (form == HK_MODES_SLOW) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r[v] = hk_modes_slow(xv[v], x0v[v], rc.a, cnt, rc.eps);
+  } else {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) r[v] = -0.0f;  // -2 pi * (empty sum) / (1 + eps), whatever x is
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) score_hk_stream_kernel(const float* __restrict__ x, const float* __restrict__ x0,
+                                                              float* __restrict__ out, const HkRec* __restrict__ rec,
+                                                              const unsigned char* __restrict__ order, unsigned int nvec,
+                                                              unsigned int vps /* vectors per sample */, int D) {
+  const unsigned int vpt = HK_TILE * vps;  // vectors per sorting tile
+  const unsigned int stride = gridDim.x * blockDim.x;
+  unsigned int v = blockIdx.x * blockDim.x + threadIdx.x;
+  struct Item { size_t off; HkRec rc; float xv[VEC], x0v[VEC]; };
+  auto fetch = [&](unsigned int vi, Item& it) {
+    const unsigned int tile = vi / vpt, w = vi - tile * vpt;
+    const unsigned int slot = w / vps, j = w - slot * vps;
+    const size_t s = static_cast<size_t>(tile) * HK_TILE + order[static_cast<size_t>(tile) * HK_TILE + slot];
+    it.off = s * D + j * VEC;
+    const int4 rr = __ldg(reinterpret_cast<const int4*>(rec + s));
+    it.rc.a = __int_as_float(rr.x); it.rc.b = __int_as_float(rr.y); it.rc.eps = __int_as_float(rr.z); it.rc.fc = rr.w;
+    if (VEC == 1) {
+      it.xv[0] = x[it.off];
+      it.x0v[0] = x0[it.off];
+    } else {
+#pragma unroll
+      for (int h = 0; h < VEC / 4; ++h) {
+        const float4 a = ld_stream4(x + it.off + 4 * h), b = ld_stream4(x0 + it.off + 4 * h);
+        it.xv[(4 * h) % VEC] = a.x; it.xv[(4 * h + 1) % VEC] = a.y; it.xv[(4 * h + 2) % VEC] = a.z; it.xv[(4 * h + 3) % VEC] = a.w;
+        it.x0v[(4 * h) % VEC] = b.x; it.x0v[(4 * h + 1) % VEC] = b.y; it.x0v[(4 * h + 2) % VEC] = b.z; it.x0v[(4 * h + 3) % VEC] = b.w;
+      }
+    }
+  };
+  if (v >= nvec) return;
+  Item cur, nxt;
+  fetch(v, cur);
+  for (;;) {
+    const unsigned int vn = v + stride;
+    const bool more = vn < nvec && vn > v;
+    if (more) fetch(vn, nxt);
+    float r[VEC];
+    hk_eval<VEC>(cur.xv, cur.x0v, cur.rc, r);
+    if (VEC == 1) {
+      out[cur.off] = r[0];
+    } else {
+#pragma unroll
+      for (int h = 0; h < VEC / 4; ++h)
+        st_stream4(out + cur.off + 4 * h, make_float4(r[(4 * h) % VEC], r[(4 * h + 1) % VEC], r[(4 * h + 2) % VEC], r[(4 * h + 3) % VEC]));
+    }
+    if (!more) break;
+    cur = nxt;
+    v = vn;
   }
 }
 
@@ -615,25 +870,63 @@ int rd_score_hk_f32(const float* x, const float* x_orig, const float* sigma, flo
   RD_REQUIRE(refls >= 0, "rd_score_hk_f32: refls must be >= 0");
   RD_REQUIRE(D <= (1u << 20), "rd_score_hk_f32: D too large");
   size_t blocks = (B + HK_SPB - 1) / HK_SPB;
-  bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_orig) |
-                               reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-  // block size: the one (multiple of 32, 128..256) that leaves the fewest idle threads in the last pass over the
-  // block's HK_SPB * D elements (D = 72: 576 vectors = 3 passes of 192 threads)
-  const size_t items = static_cast<size_t>(HK_SPB) * D / (vec ? 4 : 1);
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_orig) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int vec = (aligned16 && D % 8 == 0) ? 8 : ((aligned16 && D % 4 == 0) ? 4 : 1);
+  // block size: the one (multiple of 32, 128..288) that leaves the fewest idle threads in the last pass over the
+  // block's HK_SPB * D elements (D = 72, 8 elements per thread: 288 threads, exactly one pass)
+  const size_t items = static_cast<size_t>(HK_SPB) * D / vec;
   int threads = 256;
   double best = 0.0;
-  for (int t = 256; t >= 128; t -= 32) {
+  for (int t = 288; t >= 128; t -= 32) {
     const double eff = static_cast<double>(items) / (static_cast<double>((items + t - 1) / t) * t);
     if (eff > best + 1e-9) { best = eff; threads = t; }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (vec)
+  if (vec == 8)
+    score_hk_kernel<8><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
+                                                                           static_cast<int>(D), efs, refls, min_cutoff);
+  else if (vec == 4)
     score_hk_kernel<4><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
                                                                            static_cast<int>(D), efs, refls, min_cutoff);
   else
     score_hk_kernel<1><<<static_cast<unsigned>(blocks), threads, 0, st>>>(x, x_orig, sigma, sigma_scalar, out, B,
                                                                            static_cast<int>(D), efs, refls, min_cutoff);
   return check_launch("score_hk_kernel");
+}
+
+size_t rd_score_hk_workspace_bytes(size_t B) { return (B + HK_TILE - 1) / HK_TILE * HK_TILE * (sizeof(HkRec) + 1) + 256; }
+
+int rd_score_hk_ws_f32(const float* x, const float* x_orig, const float* sigma, float sigma_scalar, float* out, size_t B,
+                       size_t D, int efs, int refls, float min_cutoff, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0 || D == 0) return RD_OK;
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_orig) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int vec = (aligned16 && D % 8 == 0) ? 8 : ((aligned16 && D % 4 == 0) ? 4 : 1);
+  const size_t nvec = B * (D / vec);
+  if (!workspace || workspace_bytes < rd_score_hk_workspace_bytes(B) || nvec >= (1ull << 31) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return rd_score_hk_f32(x, x_orig, sigma, sigma_scalar, out, B, D, efs, refls, min_cutoff, stream);  // single-kernel path
+  RD_REQUIRE(x && x_orig && out, "rd_score_hk_ws_f32: null pointer");
+  RD_REQUIRE(efs >= 0 && efs <= HK_MAX_EFS, "rd_score_hk_ws_f32: efs must be in [0,%d]", HK_MAX_EFS);
+  RD_REQUIRE(refls >= 0, "rd_score_hk_ws_f32: refls must be >= 0");
+  RD_REQUIRE(D <= (1u << 20), "rd_score_hk_ws_f32: D too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HkRec* rec = static_cast<HkRec*>(workspace);
+  unsigned char* order = reinterpret_cast<unsigned char*>(rec + (B + HK_TILE - 1) / HK_TILE * HK_TILE);
+  hk_prepare_kernel<<<static_cast<unsigned>((B + HK_TILE - 1) / HK_TILE), HK_TILE, 0, st>>>(sigma, sigma_scalar, B, efs, refls, min_cutoff, rec,
+                                                                                      order);
+  int rc = check_launch("hk_prepare_kernel");
+  if (rc != RD_OK) return rc;
+  // one resident wave: 148 SMs x 8 blocks of 256 threads, each thread walks its vectors with the next one in flight
+  size_t blocks = (nvec + 255) / 256;
+  if (blocks > static_cast<size_t>(kNumSMs) * 8) blocks = static_cast<size_t>(kNumSMs) * 8;
+  const unsigned int nv = static_cast<unsigned int>(nvec), vps = static_cast<unsigned int>(D / vec);
+  if (vec == 8)
+    score_hk_stream_kernel<8><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, x_orig, out, rec, order, nv, vps, static_cast<int>(D));
+  else if (vec == 4)
+    score_hk_stream_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, x_orig, out, rec, order, nv, vps, static_cast<int>(D));
+  else
+    score_hk_stream_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, x_orig, out, rec, order, nv, vps, static_cast<int>(D));
+  return check_launch("score_hk_stream_kernel");
 }
 
 int rd_philox_normal_f32(float* out, size_t n, uint64_t seed, uint32_t draw, void* stream) {

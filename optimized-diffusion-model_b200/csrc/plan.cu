@@ -80,6 +80,28 @@ static int enqueue_iteration(rd_sampler* s, cudaStream_t st, int* launches) {
 
 extern "C" {
 
+// ---- unit entry points: one reference layer per call on caller-owned buffers (layer-level parity tests, and the
+// `forward` of the drop-in's ResnetBlockDDPMpp / AttnBlockpp modules)
+int rd_resblock(const rd_op_temb* temb, const rd_op_conv* shortcut, const rd_op_conv* conv0, const rd_op_conv* conv1, int n_slices,
+                void* stream) {
+  RD_REQUIRE(conv0 && conv1 && n_slices >= 1, "rd_resblock: conv0 / conv1 are required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (temb && (rc = temb_launch(*temb, st)) != RD_OK) return rc;                    // Dense_0(act(temb)) -> conv0's additive rows
+  for (int i = 0; shortcut && i < n_slices; ++i)
+    if ((rc = conv_launch(shortcut[i], st)) != RD_OK) return rc;                     // NIN_0 when the channel count changes
+  for (int i = 0; i < n_slices; ++i)
+    if ((rc = conv_launch(conv0[i], st)) != RD_OK) return rc;                        // GN0 + SiLU + Conv_0 + temb rows
+  for (int i = 0; i < n_slices; ++i)
+    if ((rc = conv_launch(conv1[i], st)) != RD_OK) return rc;                        // GN1 + SiLU + Conv_1 + skip, * out_scale
+  return RD_OK;
+}
+
+int rd_attn_block(const rd_op_attn_block* op, void* stream) {
+  RD_REQUIRE(op, "rd_attn_block: null op");
+  return attn_block_launch(*op, static_cast<cudaStream_t>(stream));
+}
+
 int rd_plan_create(rd_plan** out) {
   RD_REQUIRE(out, "rd_plan_create: null out");
   *out = new (std::nothrow) rd_plan();

@@ -1,6 +1,8 @@
-"""NCSN++ building blocks of the drop-in (reference models/layerspp.py:19-28, 67-214): parameter
-containers with the reference's attribute names.  Their arithmetic is executed by the fused CUDA
-plan (GN+SiLU -> tcgen05 conv -> temb/skip epilogue), not module by module.
+"""NCSN++ building blocks of the drop-in (reference models/layerspp.py:19-28, 67-214): the reference's
+attribute names (so state_dicts match).  Inside NCSNpp their arithmetic is executed by the fused CUDA
+plan (GN+SiLU -> tcgen05 conv -> temb/skip epilogue), not module by module; called on their own,
+`ResnetBlockDDPMpp.forward` / `AttnBlockpp.forward` run the same kernels through the unit entry
+points `rd_resblock` / `rd_attn_block` (rdb200/unit.py).  CUDA only, inference only.
 """
 import torch
 import torch.nn as nn
@@ -34,6 +36,11 @@ class AttnBlockpp(nn.Module):
         self.NIN_0, self.NIN_1, self.NIN_2 = NIN(channels, channels), NIN(channels, channels), NIN(channels, channels)
         self.NIN_3 = NIN(channels, channels, init_scale=init_scale)
         self.skip_rescale = skip_rescale
+
+    def forward(self, x):
+        """x [B,C,H,W] fp32 CUDA -> (x + attn(x)) [/ sqrt 2] (layerspp.py:80-96), one fused kernel."""
+        from rdb200 import unit
+        return unit.attnblock_forward(self, x)
 
 
 class _Resample(nn.Module):
@@ -85,3 +92,11 @@ class ResnetBlockDDPMpp(nn.Module):
         if in_ch != out_ch:
             self.NIN_0 = NIN(in_ch, out_ch)
         self.skip_rescale, self.act, self.out_ch, self.conv_shortcut = skip_rescale, act, out_ch, conv_shortcut
+        self.rd_precision = "bf16"  # "fp32": the fp32-class kernels (split-bf16 tensor-core operands)
+
+    def forward(self, x, temb=None):
+        """x [B,C_in,H,W] fp32 CUDA, temb [B,temb_dim] or None -> [B,C_out,H,W] (layerspp.py:198-214, eval mode)."""
+        if not isinstance(self.act, nn.SiLU):
+            raise NotImplementedError('the B200 kernels fuse swish/SiLU only')
+        from rdb200 import unit
+        return unit.resblock_forward(self, x, temb, precision=self.rd_precision)

@@ -29,6 +29,9 @@ SIGNATURES = {
     "rd_inside_f32": (C.c_int, [c_vp, c_vp, C.c_size_t, C.c_size_t, c_vp]),
     "rd_score_hk_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_float, c_vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                   C.c_float, c_vp]),
+    "rd_score_hk_workspace_bytes": (C.c_size_t, [C.c_size_t]),
+    "rd_score_hk_ws_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_float, c_vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                     C.c_float, c_vp, C.c_size_t, c_vp]),
     "rd_philox_normal_f32": (C.c_int, [c_vp, C.c_size_t, C.c_uint64, C.c_uint32, c_vp]),
     "rd_pc_norms": (C.c_int, [c_vp, c_vp, c_vp, C.POINTER(C.c_int), C.c_size_t, C.c_size_t, C.c_uint64,
                               C.c_uint32, c_vp, C.c_size_t, c_vp]),
@@ -42,6 +45,8 @@ SIGNATURES = {
     "rd_pf_drift_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_float, C.c_float, c_vp, C.c_size_t, C.c_size_t, c_vp]),
     "rd_gto_halo_decode_f32": (C.c_int, [c_vp, c_vp, C.c_size_t, C.c_size_t, c_vp, c_vp]),
     "rd_gto_halo_encode_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, C.c_float, c_vp]),
+    "rd_resblock": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
+    "rd_attn_block": (C.c_int, [c_vp, c_vp]),
     "rd_plan_create": (C.c_int, [C.POINTER(c_vp)]),
     "rd_plan_add": (C.c_int, [c_vp, c_vp]),
     "rd_plan_size": (C.c_int, [c_vp]),
@@ -50,6 +55,7 @@ SIGNATURES = {
     "rd_plan_destroy": (C.c_int, [c_vp]),
     "rd_conv_launch_info": (C.c_int, [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rd_checksum_f32": (C.c_int, [c_vp, C.c_int, c_vp, c_vp]),
+    "rd_conv_geometry": (C.c_int, [c_vp, C.POINTER(C.c_int)]),
     "rd_sampler_create": (C.c_int, [c_vp, C.POINTER(c_vp)]),
     "rd_sampler_run": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "rd_sampler_launches_per_iter": (C.c_int, [c_vp]),

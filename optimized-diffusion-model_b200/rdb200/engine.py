@@ -139,6 +139,7 @@ class Engine:
         self._temb_op_index = 0
         self.op_names: List[str] = []
         self.op_kinds: Dict[str, str] = {}
+        self.op_info: Dict[str, dict] = {}  # conv launches: tile geometry + algorithmic flops (profiling feedback)
         self.conv_flops_per_sample = 0.0  # algorithmic 2*M*N*K of the tcgen05 launches, valid pixels only
         self.attn_flops_per_sample = 0.0  # QK^T + PV of the stand-alone attention core launches
         self.tensors: Dict[str, _Act] = {}
@@ -154,6 +155,15 @@ class Engine:
     def _add(self, op: D.Op, name: str):
         check(lib().rd_plan_add(self.plan, C.byref(op)), f"rd_plan_add({name})")
         self.op_names.append(name)
+        if op.kind == D.RD_OP_CONV:
+            geom = (C.c_int * 12)()
+            check(lib().rd_conv_geometry(C.byref(op.u.conv), geom), "rd_conv_geometry")
+            c = op.u.conv
+            self.op_info[name] = dict(zip(("S", "n_tiles", "R", "n_groups", "a_stages", "w_resident", "w_stages", "acc_bufs",
+                                           "xmode", "smem", "grid", "tmem_cols"), list(geom)),
+                                      cin=sum(c.src[i].C for i in range(c.nsrc)), n=c.C_out, taps=c.ntaps, hw=(c.H_in, c.W_in),
+                                      flops=2.0 * c.H_out * c.W_out * c.C_out * sum(c.src[i].C for i in range(c.nsrc)) * c.ntaps,
+                                      res=bool(c.residual), gn=c.gn_groups > 0)
         self.op_kinds[name] = {D.RD_OP_CONV: "conv", D.RD_OP_ATTN_CORE: "attn", D.RD_OP_TEMB: "temb",
                                D.RD_OP_IN_CONV: "in_conv", D.RD_OP_OUT_HEAD: "out_head", D.RD_OP_ATTN_BLOCK: "attn_block"}[op.kind]
 

@@ -40,9 +40,24 @@ def score_hk(x, x_orig, sigma, efs: int = 20, refls: int = 10, min_cutoff: float
         sp, ss = ptr(sig), 0.0
     else:
         sp, ss = None, float(sigma)
-    check(lib().rd_score_hk_f32(ptr(x), ptr(x_orig), sp, ss, ptr(out), B, D, int(efs), int(refls),
-                                float(min_cutoff), stream_ptr(x.device)), "rd_score_hk_f32")
+    ws = _hk_workspace(x.device, B)
+    check(lib().rd_score_hk_ws_f32(ptr(x), ptr(x_orig), sp, ss, ptr(out), B, D, int(efs), int(refls), float(min_cutoff),
+                                   ptr(ws), ws.numel(), stream_ptr(x.device)), "rd_score_hk_ws_f32")
     return out
+
+
+_HK_WS = {}
+
+
+def _hk_workspace(device, B: int) -> torch.Tensor:
+    """Per-device scratch for the streaming score_hk path (17 bytes per sample), grown on demand and reused: calls
+    on one stream are ordered, so the pre-pass of a call cannot overtake the previous call's readers."""
+    need = int(lib().rd_score_hk_workspace_bytes(B))
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _HK_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _HK_WS[key] = torch.empty((max(need, 1 << 16),), dtype=torch.uint8, device=device)
+    return ws
 
 
 def philox_normal(shape, seed: int, draw: int, device) -> torch.Tensor:

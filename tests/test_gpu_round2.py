@@ -222,3 +222,57 @@ def test_weight_swap_detection_is_content_based():
         assert torch.equal(y2, y0)
         with model.rd_freeze_weights():                    # inside a frozen region the check is skipped by contract
             assert model.rd_sync_weights() is False
+
+
+# ------------------------------------------------------------------------------------------------ stand-alone layers
+@pytest.mark.parametrize("cin,cout,hw,precision", [(64, 64, (8, 9), "bf16"), (64, 128, (4, 4), "bf16"), (128, 128, (2, 2), "fp32"),
+                                                     (64, 64, (9, 9), "fp32"), (256, 256, (4, 4), "bf16")])
+def test_resblock_forward_standalone(cin, cout, hw, precision):
+    """ResnetBlockDDPMpp.forward(x, temb) on its own (layerspp.py:198-214) through rd_resblock."""
+    import torch.nn as nn
+    from models import layerspp
+    torch.manual_seed(5)
+    blk = layerspp.ResnetBlockDDPMpp(nn.SiLU(), cin, cout, temb_dim=256, skip_rescale=True, init_scale=1.0).to(DEV).eval()
+    blk.rd_precision = precision
+    with torch.no_grad():
+        for p in blk.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {"b." + k: v.detach() for k, v in blk.state_dict().items()}
+    B = 5
+    x = torch.randn(B, cin, *hw, device=DEV)
+    temb = torch.randn(B, 256, device=DEV)
+    y = blk(x, temb)
+    with torch.no_grad():
+        ref = O.resblock(x, temb, sd, "b", True)
+    e = rel_to_max(y, ref)
+    print(f"resblock {cin}->{cout} {hw} {precision}: rel-to-max err {e:.3e}")
+    assert y.shape == ref.shape and e <= (3e-5 if precision == "fp32" else 1.5e-2)
+    y2 = blk(x)   # temb=None: no Dense_0 term at all (layerspp.py:201: `if temb is not None`)
+    sd0 = dict(sd)
+    sd0["b.Dense_0.weight"], sd0["b.Dense_0.bias"] = torch.zeros_like(sd["b.Dense_0.weight"]), torch.zeros_like(sd["b.Dense_0.bias"])
+    with torch.no_grad():
+        ref2 = O.resblock(x, temb, sd0, "b", True)
+    assert rel_to_max(y2, ref2) <= (3e-5 if precision == "fp32" else 1.5e-2)
+
+
+def test_attnblock_forward_standalone():
+    """AttnBlockpp.forward(x) on its own (layerspp.py:80-96) through rd_attn_block."""
+    from models import layerspp
+    torch.manual_seed(6)
+    blk = layerspp.AttnBlockpp(64, skip_rescale=True, init_scale=1.0).to(DEV).eval()
+    with torch.no_grad():
+        for p in blk.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {"a." + k: v.detach() for k, v in blk.state_dict().items()}
+    for hw in ((8, 9), (9, 9), (4, 4)):
+        x = torch.randn(7, 64, *hw, device=DEV)
+        y = blk(x)
+        with torch.no_grad():
+            ref = O.attnblock(x, sd, "a", True)
+        e = rel_to_max(y, ref)
+        print(f"attnblock {hw}: rel-to-max err {e:.3e}")
+        assert e <= 1.5e-2
+    with pytest.raises(NotImplementedError):
+        layerspp.AttnBlockpp(128).to(DEV)(torch.randn(1, 128, 8, 9, device=DEV))

@@ -102,8 +102,9 @@ def run(args, dev=None, quiet=False):
             sig = torch.full((B,), s, device=dev)
         torch.addcmul(mean, sig.view(-1, 1, 1, 1), z, out=xin)
         check(L.rd_reflect_f32(ptr(xin), ptr(xin), n, st), "reflect")   # x = reflect(mean + sigma z), in place
-        a, m = timed(lambda: check(L.rd_score_hk_f32(ptr(xin), ptr(mean), ptr(sig), 0.0, ptr(out), B, D, 20, 10, 1e-2, st),
-                                   "score_hk"), args.reps)
+        ws = torch.empty((int(L.rd_score_hk_workspace_bytes(B)),), dtype=torch.uint8, device=dev)
+        a, m = timed(lambda: check(L.rd_score_hk_ws_f32(ptr(xin), ptr(mean), ptr(sig), 0.0, ptr(out), B, D, 20, 10, 1e-2,
+                                                        ptr(ws), ws.numel(), st), "score_hk"), args.reps)
         emit("score_hk " + name, a, m, 12 * n + 4 * B, {"finite": bool(torch.isfinite(out).all())})
 
     # ---- fused sampler updates (in-kernel Philox noise, both reflections fused)
