@@ -43,6 +43,8 @@
 // product library defines none of them; results of an ablated build are garbage.
 //   RD_ABL_NO_MMA    no tcgen05.mma issued          RD_ABL_NO_EPI   epilogue does no TMEM load / math / global access
 //   RD_ABL_NO_XFORM  transform does no global load / math / st.shared   RD_ABL_NO_WSTREAM  streamed filters not copied
+//   register-cached transform only:  RD_ABL_XF_NOSTATS no statistics phase (records, reductions, their two barriers)
+//   RD_ABL_XF_NOAPPLY no normalise / SiLU arithmetic (raw pixels are stored)   RD_ABL_XF_NOLOAD no global loads
 namespace rd {
 
 constexpr int CONV_THREADS = 512;
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 
   // ------------------------------------------------------------------ setup
   if (tid == 0) {
-    for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&bar_a_full[i], 1); mbar_init(&bar_a_empty[i], 1); }
+    for (int i = 0; i < MAX_A_STAGES; ++i) { mbar_init(&bar_a_full[i], XFORM_THREADS / 32); mbar_init(&bar_a_empty[i], 1); }
     for (int i = 0; i < MAX_W_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
     fence_mbar_init();
@@ -667,39 +669,49 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     };
 
     if constexpr (RC > 0) {
-      // ---------------- register-cached mode: every thread owns one (sample, 8-channel chunk, pixel slice);
-      // its pixels are read from global memory ONCE, kept in registers across the statistics barrier,
-      // then normalised and written to the operand ring.  With RC == 8 the next group's pixels are
-      // already in flight while the current group is being normalised.
-      const int pairs = p.S * p.KC, PS = p.rc_PS;
-      const int pair = xt % pairs, slice = xt / pairs;
-      const int s = pair / p.KC, kc = pair - s * p.KC;
-      const bool owner = xt < pairs * PS;
-      const int which = (kc * 8 < p.C[0]) ? 0 : 1;
-      const int coff = kc * 8 - (which ? p.C[0] : 0);
-      const int* toff = t_off + (which ? p.S * P : 0) + s * P;
+      // ---------------- team mode (GroupNorm groups of 4 or 8 channels): a TEAM of PS adjacent lanes owns one
+      // (sample, 8-channel item) of the current 64-channel chunk and every lane RC of its pixels.  A group's statistics
+      // then live entirely inside one team, so they are a handful of warp shuffles -- no shared-memory records, no
+      // CTA-wide barrier -- and each warp hands its rows to the tensor core on its own (the operand-full barrier counts
+      // the ten transform warps).  Every pixel is read from global memory once, one (group, chunk) step ahead of use.
+      static_assert(GNM == GNM_CPG8 || GNM == GNM_CPG4, "team mode needs whole GroupNorm groups inside an 8-channel item");
+      const int PS = p.rc_PS, ps_log = 31 - __clz(PS);
+      const int team = xt >> ps_log, slice = xt & (PS - 1);
+      const int s = team >> 3, kcl = team & 7;
+      const bool owner = s < p.S;
       const unsigned short* trow = t_row + s * P;
-      const int my_chunk = kc >> 3, kcl = kc & 7;
-      constexpr bool PREFETCH = (RC > 0 && RC <= 8);
-      constexpr int RCN = RC > 0 ? RC : 1;
-      uint4 raw[RCN], nxt[PREFETCH ? RCN : 1];
-      auto load_group = [&](uint4* dst, int li) {
+      const int total = my_groups * p.nchunks;
+      // RC <= 4: the next step's pixels land in a second register set while this step is processed.  Larger RC: one set
+      // (two do not fit the 128-register budget without spilling into the other roles' loops); the next step's loads are
+      // issued into the same registers right after this step's stores, so their latency overlaps the operand-stage wait.
+      constexpr bool PREFETCH = RC <= 4;
+      uint4 raw[RC], nxt[PREFETCH ? RC : 1];
+      // step st = (group li, chunk): the pixels of this lane's (sample, item) in that chunk
+      auto load_step = [&](uint4* dst, int li, int chunk) {
         const int g = blockIdx.x + li * gridDim.x;
 #ifdef RD_ABL_NO_XFORM
         const bool active = false;
 #else
         const bool active = owner && s < min(p.S, p.B2 - g * p.S);
 #endif
+        const int c0 = chunk * 64 + kcl * 8;
+        const int which = (c0 < p.C[0]) ? 0 : 1;
         const __nv_bfloat16* gbase = reinterpret_cast<const __nv_bfloat16*>(which ? src1 : src0) +
-                                     static_cast<size_t>(g) * (which ? gstride1 : gstride0) + coff;
+                                     static_cast<size_t>(g) * (which ? gstride1 : gstride0) + (c0 - (which ? p.C[0] : 0));
+        const int* toff = t_off + (which ? p.S * P : 0) + s * P;
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
-          const int px = slice + k * PS;
+          const int px = slice + (k << ps_log);
+#ifdef RD_ABL_XF_NOLOAD
+          dst[k] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+#else
           if (active && px < P) dst[k] = __ldg(reinterpret_cast<const uint4*>(gbase + toff[px]));
+#endif
         }
       };
-      if (my_groups > 0) load_group(raw, 0);
-      for (int li = 0; li < my_groups; ++li) {
+      if (total > 0) load_step(raw, 0, 0);
+      int li = 0, chunk = 0;
+      for (int st = 0; st < total; ++st, ++a_it) {
         const int g = blockIdx.x + li * gridDim.x;
         const int S_act = max(0, min(p.S, p.B2 - g * p.S));
 #ifdef RD_ABL_NO_XFORM
@@ -707,48 +719,78 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
 #else
         const bool active = owner && s < S_act;
 #endif
-        if (!PREFETCH && li > 0) load_group(raw, li);
-        float sum[8], sq[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; sq[j] = 0.0f; }
-#pragma unroll
-        for (int k = 0; k < RC; ++k) {
-          if (active && slice + k * PS < P) {
-            float f[8];
-            unpack8(raw[k], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] = fmaf(f[j], f[j], sq[j]); }
-          }
-        }
-        if (owner) put_record(slice * pairs + pair, sum, sq);
-        xform_bar();
-        stat_reduce(0, S_act, pairs, PS);
-        xform_bar();
-        if (PREFETCH && li + 1 < my_groups) load_group(nxt, li + 1);
+        int li_n = li, chunk_n = chunk + 1;
+        if (chunk_n == p.nchunks) { chunk_n = 0; ++li_n; }
+        if (PREFETCH && st + 1 < total) load_step(nxt, li_n, chunk_n);
+        // ---- statistics of this lane's pixels: (sum, sum of squares) of channels 0-3 and 4-7, then over the team
         float ca[8], cb[8];
-        if (active) gn_coeffs(s, kc * 8, ca, cb);
-        for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
-          const int stage = a_it % p.a_stages;
-          if (a_it >= p.a_stages) mbar_wait_relaxed(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
-          if (active && chunk == my_chunk) {
-            uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes) + kcl * p.R;
+#ifndef RD_ABL_XF_NOSTATS
+        {
+          float s_lo = 0.0f, q_lo = 0.0f, s_hi = 0.0f, q_hi = 0.0f;
 #pragma unroll
-            for (int k = 0; k < RC; ++k) {
-              const int px = slice + k * PS;
-              if (px < P) {
-                gn_apply(raw[k], ca, cb);
-                a4[trow[px]] = raw[k];
+          for (int k = 0; k < RC; ++k) {
+            if (active && slice + (k << ps_log) < P) {
+              float f[8];
+              unpack8(raw[k], f);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                s_lo += f[j]; q_lo = fmaf(f[j], f[j], q_lo);
+                s_hi += f[4 + j]; q_hi = fmaf(f[4 + j], f[4 + j], q_hi);
               }
             }
           }
-          fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
-          xform_bar();
-          if (xt == 0) mbar_arrive(&bar_a_full[stage]);
+          if (GNM == GNM_CPG8) { s_lo += s_hi; q_lo += q_hi; }
+          for (int o = PS >> 1; o > 0; o >>= 1) {  // teams are aligned power-of-two lane groups: fixed-order butterfly
+            s_lo += __shfl_xor_sync(0xffffffffu, s_lo, o);
+            q_lo += __shfl_xor_sync(0xffffffffu, q_lo, o);
+            if (GNM == GNM_CPG4) {
+              s_hi += __shfl_xor_sync(0xffffffffu, s_hi, o);
+              q_hi += __shfl_xor_sync(0xffffffffu, q_hi, o);
+            }
+          }
+          const float m_lo = s_lo * inv_n, m_hi = GNM == GNM_CPG8 ? m_lo : s_hi * inv_n;
+          const float r_lo = 1.0f / sqrtf(fmaxf(q_lo * inv_n - m_lo * m_lo, 0.0f) + p.eps);
+          const float r_hi = GNM == GNM_CPG8 ? r_lo : 1.0f / sqrtf(fmaxf(q_hi * inv_n - m_hi * m_hi, 0.0f) + p.eps);
+          const int c0 = chunk * 64 + kcl * 8;
+          const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + c0), g1 = *reinterpret_cast<const float4*>(s_gamma + c0 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(s_beta + c0), b1 = *reinterpret_cast<const float4*>(s_beta + c0 + 4);
+          const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float hs = p.silu ? 0.5f : 1.0f;  // SiLU(y) = h + h tanh(h), h = y / 2: the halving is folded into the affine
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ca[j] = gam[j] * (j < 4 ? r_lo : r_hi) * hs;
+            cb[j] = fmaf(-(j < 4 ? m_lo : m_hi), ca[j], bet[j] * hs);
+          }
         }
+#else
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ca[j] = 0.5f; cb[j] = 0.0f; }
+#endif
+        const int stage = a_it % p.a_stages;
+        if (a_it >= p.a_stages) mbar_wait_relaxed(&bar_a_empty[stage], ((a_it / p.a_stages) - 1) & 1);
+        if (active) {
+          uint4* a4 = reinterpret_cast<uint4*>(As + stage * p.a_stage_bytes) + kcl * p.R;
+#pragma unroll
+          for (int k = 0; k < RC; ++k) {
+            const int px = slice + (k << ps_log);
+            if (px < P) {
+#ifndef RD_ABL_XF_NOAPPLY
+              gn_apply(raw[k], ca, cb);
+#endif
+              a4[trow[px]] = raw[k];
+            }
+          }
+        }
+        if (!PREFETCH && st + 1 < total) load_step(raw, li_n, chunk_n);
+        fence_proxy_async_smem();  // st.shared above must be visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_a_full[stage]);
         if (PREFETCH) {
 #pragma unroll
           for (int k = 0; k < RC; ++k) raw[k] = nxt[k];
         }
+        li = li_n; chunk = chunk_n;
       }
     } else if constexpr (GNM == GNM_NONE && !X3) {
       // ---------------- plain gather (NIN shortcuts, up/down-sampling convs, attention projections): there is nothing
@@ -782,8 +824,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       for (int it = 0; it < total; ++it) {
         if (it + 1 < total) { issue_chunk(it + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         fence_proxy_async_smem();
-        xform_bar();
-        if (xt == 0) mbar_arrive(&bar_a_full[it % p.a_stages]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_a_full[it % p.a_stages]);  // every transform warp reports its own rows
       }
     } else {
       // ---------------- streaming mode: statistics pass, then a normalise pass per chunk (also the only transform of
@@ -885,8 +927,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             }
           }
           fence_proxy_async_smem();
-          xform_bar();
-          if (xt == 0) mbar_arrive(&bar_a_full[stage]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_a_full[stage]);
         }
       }
     }
@@ -1027,13 +1069,14 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
       if (conv_smem_layout(c).total > smem_cap) c.a_stages = 1;  // last resort (fp32-class plan at 16x16): transform and MMAs alternate
       if (conv_smem_layout(c).total > smem_cap) continue;
     }
-    // transform mode: register-cached when every (sample, chunk) pair gets a thread and <= 16 pixels (bf16 only)
+    // transform mode: team mode (bf16 plan, GroupNorm groups of 4 / 8 channels) when the S x 8 (sample, item) teams of a
+    // chunk fit the 320 transform threads with at most 16 pixels per lane; otherwise the two-pass streaming transform
     c.xmode = 0; c.rc_PS = 1;
-    if (!p.x3 && p.groups > 0 && c.S * p.KC <= XFORM_THREADS) {
-      int ps = XFORM_THREADS / (c.S * p.KC);
-      if (ps > p.H * p.W) ps = p.H * p.W;
+    if (!p.x3 && p.groups > 0 && (p.cpg == 4 || p.cpg == 8) && c.S * 8 <= XFORM_THREADS) {
+      int ps = 1;
+      while (ps < 32 && c.S * 8 * (ps * 2) <= XFORM_THREADS) ps *= 2;
       const int slots = (p.H * p.W + ps - 1) / ps;
-      if (slots <= 16) { c.xmode = slots <= 8 ? 8 : 16; c.rc_PS = ps; }
+      if (slots <= 16) { c.xmode = slots <= 4 ? 4 : (slots <= 9 ? 9 : 16); c.rc_PS = ps; }
     }
     double score = static_cast<double>(c.S * valid_px) / (nt * 128);
     if (c.acc_bufs == 1) score *= 0.75;
@@ -1067,14 +1110,14 @@ static conv_kernel_t conv_pick(int gnm, int rc, int x3) {
   switch (gnm * 100 + rc) {
     case GNM_NONE * 100 + 0: return RD_K(GNM_NONE, 0);
     case GNM_CPG8 * 100 + 0: return RD_K(GNM_CPG8, 0);
-    case GNM_CPG8 * 100 + 8: return RD_K(GNM_CPG8, 8);
+    case GNM_CPG8 * 100 + 4: return RD_K(GNM_CPG8, 4);
+    case GNM_CPG8 * 100 + 9: return RD_K(GNM_CPG8, 9);
     case GNM_CPG8 * 100 + 16: return RD_K(GNM_CPG8, 16);
     case GNM_CPG4 * 100 + 0: return RD_K(GNM_CPG4, 0);
-    case GNM_CPG4 * 100 + 8: return RD_K(GNM_CPG4, 8);
+    case GNM_CPG4 * 100 + 4: return RD_K(GNM_CPG4, 4);
+    case GNM_CPG4 * 100 + 9: return RD_K(GNM_CPG4, 9);
     case GNM_CPG4 * 100 + 16: return RD_K(GNM_CPG4, 16);
     case GNM_GENERAL * 100 + 0: return RD_K(GNM_GENERAL, 0);
-    case GNM_GENERAL * 100 + 8: return RD_K(GNM_GENERAL, 8);
-    case GNM_GENERAL * 100 + 16: return RD_K(GNM_GENERAL, 16);
     default: return nullptr;
   }
 #undef RD_K

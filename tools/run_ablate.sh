@@ -5,13 +5,14 @@ TAG=${1:-abl}
 mkdir -p gpurun_out
 L=$PWD/optimized-diffusion-model_b200/rdb200
 timeout 300 python tools/gpu_optime.py > gpurun_out/${TAG}_product.log 2>&1; echo "product rc=$?"
-for v in NO_MMA NO_EPI NO_XFORM NO_WSTREAM; do
+for v in ${ABL_VARIANTS:-NO_MMA NO_EPI NO_XFORM NO_WSTREAM}; do
   RDB200_LIB=$L/librdb200_abl_$v.so timeout 300 python tools/gpu_optime.py > gpurun_out/${TAG}_$v.log 2>&1; echo "$v rc=$?"
 done
 python - <<PY
 import re
 rows = {}
-names = ["product", "NO_MMA", "NO_EPI", "NO_XFORM", "NO_WSTREAM"]
+import os
+names = ["product"] + os.environ.get("ABL_VARIANTS", "NO_MMA NO_EPI NO_XFORM NO_WSTREAM").split()
 order = []
 for v in names:
     for ln in open("gpurun_out/${TAG}_%s.log" % v):
@@ -19,7 +20,7 @@ for v in names:
         if m:
             rows.setdefault(m.group(1), {})[v] = float(m.group(2))
             if v == "product": order.append((m.group(1), ln.split("ms", 1)[1].strip()[:110]))
-print("%-24s %8s %8s %8s %8s %8s" % ("op", *names))
+print("%-24s " % "op" + " ".join("%8s" % n[-8:] for n in names))
 tot = {v: 0.0 for v in names}
 for n, info in order:
     r = rows[n]
