@@ -25,6 +25,7 @@
  *   rd_perturb_reflect_f32    x_t = cube.reflect(mean + std z)      losses.py:80-82
  *   rd_dsm_reduce_f32         weighted squared error + reduce_op    losses.py:86-92
  *   rd_pf_drift_f32           probability-flow drift * mollifier    sampling.py:345-383, sde_lib.py:93-101
+ *   rd_rk45_stage/error_f64   scipy.integrate.solve_ivp(method='RK45') stage / error-norm arithmetic   sampling.py:383
  *   rd_gto_halo_decode_f32    latent -> physical units              ../Benchmark/gto_halo_benchmarking.py:255-328, 335-363
  *   rd_gto_halo_encode_f32    dataset row -> latent                 datasets.py:82-98 (GTOHaloImageDataset.__getitem__)
  */
@@ -113,6 +114,16 @@ int rd_dsm_reduce_f32(const float* score, const float* target, const float* weig
  * bump(x) = exp((-1/(0.25 - (0.5-x)^2) + 4) / moll) when moll > 0, else x. */
 int rd_pf_drift_f32(const float* x, const float* score, const float* g, float g_scalar, float moll, float* out,
                     size_t B, size_t D, void* stream);
+/* Device-side Dormand-Prince RK45 building blocks for get_ode_sampler (sampling.py:342-392; the reference round-trips the
+ * float64 state through scipy on the host for every right-hand side).  K: [7][n] fp32 stage derivatives.
+ *   stage:  y_out (optional) = y + (sum_{j<s} a[j] K_j) * h in fp64 ; x_out = fp32 cast of the same (the network's input)
+ *   error:  sumsq_out[0] = sum_i ((sum_j E[j] K_j[i]) * h / (atol + max(|y_i|, |y_new_i|) * rtol))^2, fixed summation order
+ *           (E has 7 entries, E[1] is zero in Dormand-Prince and not read); partial: scratch of partial_len doubles */
+int rd_rk45_stage_f64(const double* y, const float* K, size_t n, int s, const double* a, double h, double* y_out, float* x_out,
+                      void* stream);
+int rd_rk45_error_f64(const double* y, const double* y_new, const float* K, size_t n, const double* E, double h, double atol,
+                      double rtol, double* partial, int partial_len, double* sumsq_out, void* stream);
+
 /* Constants of the GTO-Halo un-normalisation; spans are (max - min). Row layout of a decoded sample:
  * [halo energy | shooting time, 2 coast times | n_triplets x (alpha, beta, r) | fuel mass, halo period, manifold length]. */
 typedef struct rd_gto_halo_codec {

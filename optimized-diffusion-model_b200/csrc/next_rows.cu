@@ -115,11 +115,91 @@ __global__ void __launch_bounds__(256) gto_halo_encode_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-side Dormand-Prince RK45 for the probability-flow ODE sampler (reference sampling.py:342-392 hands the state to
+// scipy.integrate.solve_ivp, which keeps it as a float64 numpy vector on the host and round-trips host <-> GPU for every
+// right-hand side).  Here the float64 state and the seven stage derivatives stay on the GPU; per step the host reads ONE
+// scalar (the error norm) to decide accept / reject, exactly scipy's control law.
+//   stage:  y_s = y + (sum_j a[j] K_j) * h  (fp64, scipy's order: dot first, then * h, then + y), also cast to fp32 for the network
+__global__ void __launch_bounds__(256) rk45_stage_kernel(const double* __restrict__ y, const float* __restrict__ K, size_t n, int s,
+                                                         double a0, double a1, double a2, double a3, double a4, double a5, double h,
+                                                         double* __restrict__ y_out, float* __restrict__ x_out) {
+  const double a[6] = {a0, a1, a2, a3, a4, a5};
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    double acc = 0.0;
+    for (int j = 0; j < s; ++j) acc += static_cast<double>(K[static_cast<size_t>(j) * n + i]) * a[j];
+    const double v = y[i] + acc * h;
+    if (y_out) y_out[i] = v;
+    x_out[i] = static_cast<float>(v);
+  }
+}
+
+//   error:  err = (sum_j E[j] K_j) * h ; scale = atol + max(|y|, |y_new|) * rtol ; partial[blk] = sum (err / scale)^2
+__global__ void __launch_bounds__(256) rk45_error_kernel(const double* __restrict__ y, const double* __restrict__ y_new,
+                                                         const float* __restrict__ K, size_t n, double e0, double e2, double e3,
+                                                         double e4, double e5, double e6, double h, double atol, double rtol,
+                                                         double* __restrict__ partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    const double err = (e0 * K[i] + e2 * K[2 * n + i] + e3 * K[3 * n + i] + e4 * K[4 * n + i] + e5 * K[5 * n + i] + e6 * K[6 * n + i]) * h;
+    const double sc = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+    const double r = err / sc;
+    acc += r * r;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {  // fixed-order tree: run-to-run deterministic
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void rk45_sum_kernel(const double* __restrict__ partial, int nblk, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += partial[i];
+    out[0] = s;
+  }
+}
+
 }  // namespace rd
 
 using namespace rd;
 
 extern "C" {
+
+int rd_rk45_stage_f64(const double* y, const float* K, size_t n, int s, const double* a, double h, double* y_out, float* x_out,
+                      void* stream) {
+  if (n == 0) return RD_OK;
+  RD_REQUIRE(y && x_out && (s == 0 || (K && a)) && s >= 0 && s <= 6, "rd_rk45_stage_f64: bad arguments");
+  double c[6] = {0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < s; ++j) c[j] = a[j];
+  size_t blocks = (n + 255) / 256;
+  if (blocks > static_cast<size_t>(kNumSMs) * 8) blocks = static_cast<size_t>(kNumSMs) * 8;
+  rk45_stage_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, K, n, s, c[0], c[1], c[2], c[3], c[4],
+                                                                                               c[5], h, y_out, x_out);
+  return check_launch("rk45_stage_kernel");
+}
+
+int rd_rk45_error_f64(const double* y, const double* y_new, const float* K, size_t n, const double* E, double h, double atol,
+                      double rtol, double* partial, int partial_len, double* sumsq_out, void* stream) {
+  RD_REQUIRE(y && y_new && K && E && partial && sumsq_out && n > 0 && partial_len >= 1, "rd_rk45_error_f64: bad arguments");
+  size_t blocks = (n + 255) / 256;
+  if (blocks > static_cast<size_t>(partial_len)) blocks = partial_len;
+  if (blocks > static_cast<size_t>(kNumSMs) * 8) blocks = static_cast<size_t>(kNumSMs) * 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rk45_error_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(y, y_new, K, n, E[0], E[2], E[3], E[4], E[5], E[6], h, atol, rtol, partial);
+  int rc = check_launch("rk45_error_kernel");
+  if (rc != RD_OK) return rc;
+  rk45_sum_kernel<<<1, 32, 0, st>>>(partial, static_cast<int>(blocks), sumsq_out);
+  return check_launch("rk45_sum_kernel");
+}
 
 int rd_gto_halo_encode_f32(const float* raw, float* latents, float* labels, size_t n, size_t n_in, size_t n_latent,
                            float data_mean, float data_std, void* stream) {

@@ -47,6 +47,9 @@ SIGNATURES = {
     "rd_gto_halo_encode_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_float, C.c_float, c_vp]),
     "rd_resblock": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
     "rd_attn_block": (C.c_int, [c_vp, c_vp]),
+    "rd_rk45_stage_f64": (C.c_int, [c_vp, c_vp, C.c_size_t, C.c_int, c_vp, C.c_double, c_vp, c_vp, c_vp]),
+    "rd_rk45_error_f64": (C.c_int, [c_vp, c_vp, c_vp, C.c_size_t, c_vp, C.c_double, C.c_double, C.c_double, c_vp, C.c_int, c_vp,
+                                    c_vp]),
     "rd_plan_create": (C.c_int, [C.POINTER(c_vp)]),
     "rd_plan_add": (C.c_int, [c_vp, c_vp]),
     "rd_plan_size": (C.c_int, [c_vp]),
