@@ -23,8 +23,9 @@ A_ROWS = [np.array(r, dtype=np.float64) for r in (
     [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656])]
 B_ROW = np.array([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84], dtype=np.float64)
 E_ROW = np.array([-71 / 57600, 0, 71 / 16695, -71 / 1920, 17253 / 339200, -22 / 525, 1 / 40], dtype=np.float64)
-SAFETY, MIN_FACTOR, MAX_FACTOR, ORDER = 0.9, 0.2, 10.0, 5   # error estimator order 4 -> exponent -1/(4+1)
-ERROR_EXPONENT = -1.0 / 5.0
+SAFETY, MIN_FACTOR, MAX_FACTOR = 0.9, 0.2, 10.0
+ERROR_ESTIMATOR_ORDER = 4
+ERROR_EXPONENT = -1.0 / (ERROR_ESTIMATOR_ORDER + 1)
 
 
 def _dptr(a: np.ndarray):
@@ -85,14 +86,14 @@ class DeviceRK45:
         if d1 <= 1e-15 and d2 <= 1e-15:
             h1 = max(1e-6, h0 * 1e-3)
         else:
-            h1 = (0.01 / max(d1, d2)) ** (1.0 / (ORDER + 1 - 1))   # error_estimator_order = 4: exponent 1 / (4 + 1)
+            h1 = (0.01 / max(d1, d2)) ** (1.0 / (ERROR_ESTIMATOR_ORDER + 1))
         return min(100 * h0, h1, interval)
 
     def step(self) -> bool:
         """RungeKutta._step_impl: attempt steps until one is accepted (True) or the step size underflows (False)."""
         t, st = self.t, stream_ptr(self.dev)
         min_step = 10 * abs(np.nextafter(t, self.direction * np.inf) - t)
-        h_abs = min(max(self.h_abs, min_step), abs(self.t_bound - t)) if self.h_abs > abs(self.t_bound - t) else max(self.h_abs, min_step)
+        h_abs = max(self.h_abs, min_step)   # (max_step is infinite: solve_ivp's default)
         rejected = False
         while True:
             if h_abs < min_step:

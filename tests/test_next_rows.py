@@ -210,10 +210,19 @@ def test_ode_sampler_vs_reference_fixture(tag):
     x0, lab = torch.from_numpy(f["x0"]).cuda(), torch.from_numpy(f["labels"]).cuda()
     fn = sampling.get_ode_sampler(sde, tuple(x0.shape), rtol=float(f["rtol"]), atol=float(f["atol"]), eps=1e-5,
                                   moll=float(f["moll"]), device="cuda")
-    x, nfe = fn(model, z=x0.clone(), weight=float(f["w"]), class_labels=lab)
+    x, nfe = fn(model, z=x0.clone(), weight=float(f["w"]), class_labels=lab)                      # device-side RK45
+    xh, nfe_h = fn(model, z=x0.clone(), weight=float(f["w"]), class_labels=lab, rd_host_solver=True)  # scipy loop, same RHS
     ref = torch.from_numpy(f["x_final"])
     err = (x.cpu() - ref).abs()
-    print("ode %s: nfe %d (reference %d) max %.3e mean %.3e" % (tag, nfe, int(f["nfe"]), float(err.max()), float(err.mean())))
+    print("ode %s: nfe %d (reference %d, scipy loop over our RHS %d) max %.3e mean %.3e | device-vs-scipy max %.3e"
+          % (tag, nfe, int(f["nfe"]), nfe_h, float(err.max()), float(err.mean()), float((x - xh).abs().max())))
+    # same scheme, same control law, same right-hand side: the device solver and scipy take the same steps
+    assert abs(nfe - nfe_h) <= max(6, 0.01 * nfe_h), (nfe, nfe_h)
+    assert float((x - xh).abs().max()) <= 1e-6
+    # (against the reference's own run the step SEQUENCE differs: with synthetic weights the mollified flow is sensitive
+    #  to 1e-5 perturbations of the right-hand side -- the fp32-class plan lands at 1772 evaluations, bf16 at 1418, the
+    #  reference at 1490 -- so the solver is pinned by the exact scipy match above and the samples by the floor below)
+    assert abs(nfe - int(f["nfe"])) <= 0.25 * int(f["nfe"]), (nfe, int(f["nfe"]))
     # floor: the oracle's own ODE run with PyTorch bf16 autocast around the network, same weights and x0
     sdg = {k: v.cuda() for k, v in sd.items()}
     sched = O.VESchedule(0.01, 5.0, 1000, 1.0, 1e-5)
