@@ -199,6 +199,13 @@ typedef struct rd_op_conv {
   int32_t out_stride;         /* 0 = C_out; otherwise channels per pixel of out / residual: a layer wider than one launch
                                  (C_out > 256, or a tile geometry that does not fit) is issued as channel slices, each
                                  with out / residual / bias / tproj_off / w advanced to its first channel */
+  /* Fused 1x1 shortcut (ResnetBlockDDPMpp's NIN_0 folded into Conv_1, layerspp.py:211-214): when sc_nsrc > 0 the RAW
+   * pixels of sc_src (gathered to H_in x W_in like src) are multiplied by the 1x1 filter slabs that follow the 3x3 slabs
+   * in `w` ([sum(sc C)/64][1][8][C_out][8]) and accumulated into the same output tile; `bias` then carries both biases
+   * and `residual` must be NULL.  bf16 plan, stride 1, GroupNorm groups of 4 or 8 channels. */
+  rd_conv_src sc_src[2];
+  int32_t sc_nsrc;
+  int32_t _pad0;
 } rd_op_conv;
 
 typedef struct rd_op_attn {

@@ -66,6 +66,12 @@ struct ConvParams {
   const void* src[2];  // bf16 (or fp32 when x3) NHWC
   int C[2], Hs[2], Ws[2];
   int nsrc;
+  // fused shortcut (ResBlock NIN_0 folded into Conv_1's launch): raw pixels of these sources are staged as sc_chunks extra
+  // 64-channel chunks after the normalised ones and multiplied by the 1x1 filter slabs that follow the 3x3 ones in `w`,
+  // into the SAME accumulator (centre tap only) -- the shortcut costs neither a launch nor a residual read
+  const void* sc_src[2];
+  int sc_C[2], sc_Hs[2], sc_Ws[2];
+  int sc_nsrc, sc_chunks;
   int H, W;          // logical (gathered) input image
   int Wp, rps;       // padded row width, rows per sample in the staged image
   int pad;           // pixel (y,x) is staged at (y+pad, x+pad)
@@ -98,6 +104,7 @@ struct ConvParams {
   void* out;
   int B2;
   unsigned char ymap[2][MAX_HW], xmap[2][MAX_HW];
+  unsigned char sc_ymap[2][MAX_HW], sc_xmap[2][MAX_HW];
 };
 
 // dynamic shared memory carve-up (bytes, every region 128-B aligned)
@@ -113,7 +120,7 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(const ConvParams& p) 
   L.a_off = 0;
   L.w_off = p.a_stages * p.a_stage_bytes;
   L.toff_off = L.w_off + (p.w_resident ? p.n_slabs : p.w_stages) * p.w_slab_bytes;
-  L.trow_off = L.toff_off + align128(2 * SP * 4);  // source element offsets [2][S*P]
+  L.trow_off = L.toff_off + align128((p.sc_chunks > 0 ? 4 : 2) * SP * 4);  // source element offsets [2 (+2 shortcut)][S*P]
   L.torow_off = L.trow_off + align128(SP * 2);     // staged row of every (sample, pixel)
   L.tos_off = L.torow_off + align128(rows * 4);    // output element offset of every accumulator row (-1: dropped)
   L.bt_off = L.tos_off + align128(rows);           // sample index of every accumulator row
@@ -357,6 +364,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     t_row[sp] = static_cast<unsigned short>(s * p.rps + (y + p.pad) * p.Wp + (x + p.pad));
     t_off[sp] = ((s * p.Hs[0] + p.ymap[0][y]) * p.Ws[0] + p.xmap[0][x]) * p.C[0];
     if (p.nsrc > 1) t_off[p.S * P + sp] = ((s * p.Hs[1] + p.ymap[1][y]) * p.Ws[1] + p.xmap[1][x]) * p.C[1];
+    if (p.sc_chunks > 0) {
+      t_off[2 * p.S * P + sp] = ((s * p.sc_Hs[0] + p.sc_ymap[0][y]) * p.sc_Ws[0] + p.sc_xmap[0][x]) * p.sc_C[0];
+      if (p.sc_nsrc > 1) t_off[3 * p.S * P + sp] = ((s * p.sc_Hs[1] + p.sc_ymap[1][y]) * p.sc_Ws[1] + p.sc_xmap[1][x]) * p.sc_C[1];
+    }
   }
   for (int row = tid; row < p.n_tiles * 128; row += CONV_THREADS) {
     const int s = row / p.rps, rem = row - s * p.rps;
@@ -386,6 +397,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     const int N = p.N, ntaps = p.ntaps, nchunks = p.nchunks, Wp = p.Wp;
     const int a_stages = p.a_stages, w_stages = p.w_stages, acc_bufs = p.acc_bufs;
     const bool w_resident = p.w_resident != 0;
+    const int sc_chunks = p.sc_chunks;
+    const uint32_t sc_shift = static_cast<uint32_t>(p.pad * (p.Wp + 1));
     const uint32_t idesc = umma_idesc_bf16(128, N);
     const uint64_t desc_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version 1
     const uint32_t a_lo0 = (smem_u32(As) >> 4) | (static_cast<uint32_t>(p.R) << 16);  // LBO = R*16 B
@@ -453,6 +466,29 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             }
           }
           if (leader) umma_commit_addr(aempty0 + 8 * stage);  // operand stage reusable once these MMAs have read it
+          if (++a_stage_i == a_stages) { a_stage_i = 0; a_par ^= 1; }
+        }
+        // fused shortcut: raw chunks x 1x1 slabs, centre tap (row shift pad * (Wp + 1)), same accumulator
+        for (int sc = 0; sc < sc_chunks; ++sc) {
+          const int stage = a_stage_i;
+          mbar_wait_addr(afull0 + 8 * stage, a_par);
+          tc_fence_after_sync();
+          const uint32_t a_lo_stage = a_lo0 + stage * a_stage_u + sc_shift;
+          if (w_resident) {
+            if (leader)
+              issue_tap<NT, TILE_OUTER, X3>(acc, uN, a_lo_stage, w_lo0 + (nchunks * NTAPS + sc) * w_slab_u, kstep_a, kstep_w, desc_hi,
+                                            idesc, 1u, a_half, w_half);
+          } else {
+            mbar_wait_addr(wfull0 + 8 * ws, w_par);
+            tc_fence_after_sync();
+            if (leader) {
+              issue_tap<NT, TILE_OUTER, X3>(acc, uN, a_lo_stage, w_lo0 + ws * w_slab_u, kstep_a, kstep_w, desc_hi, idesc, 1u, a_half,
+                                            w_half);
+              umma_commit_addr(wempty0 + 8 * ws);
+            }
+            if (++ws == w_stages) { ws = 0; w_par ^= 1; }
+          }
+          if (leader) umma_commit_addr(aempty0 + 8 * stage);
           if (++a_stage_i == a_stages) { a_stage_i = 0; a_par ^= 1; }
         }
         if (leader) umma_commit(&bar_acc_full[buf]);
@@ -680,32 +716,52 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       const int s = team >> 3, kcl = team & 7;
       const bool owner = s < p.S;
       const unsigned short* trow = t_row + s * P;
-      const int total = my_groups * p.nchunks;
+      const int steps_per_group = p.nchunks + p.sc_chunks;  // normalised chunks, then raw shortcut chunks
+      const int total = my_groups * steps_per_group;
+      const act_t* const sc0 = static_cast<const act_t*>(p.sc_src[0]);
+      const act_t* const sc1 = static_cast<const act_t*>(p.sc_src[1]);
+      const size_t sc_gstride0 = static_cast<size_t>(p.S) * p.sc_Hs[0] * p.sc_Ws[0] * p.sc_C[0];
+      const size_t sc_gstride1 = static_cast<size_t>(p.S) * p.sc_Hs[1] * p.sc_Ws[1] * p.sc_C[1];
       // RC <= 4: the next step's pixels land in a second register set while this step is processed.  Larger RC: one set
       // (two do not fit the 128-register budget without spilling into the other roles' loops); the next step's loads are
       // issued into the same registers right after this step's stores, so their latency overlaps the operand-stage wait.
       constexpr bool PREFETCH = RC <= 4;
       uint4 raw[RC], nxt[PREFETCH ? RC : 1];
       // step st = (group li, chunk): the pixels of this lane's (sample, item) in that chunk
-      auto load_step = [&](uint4* dst, int li, int chunk) {
+      // `l2_only`: warm the L2 with the step's lines instead of loading them (single-register-set variants issue this one
+      // step ahead, so that the loads they can only issue after this step's stores find their data on chip)
+      auto load_step = [&](uint4* dst, int li, int chunk, bool l2_only = false) {
         const int g = blockIdx.x + li * gridDim.x;
 #ifdef RD_ABL_NO_XFORM
         const bool active = false;
 #else
         const bool active = owner && s < min(p.S, p.B2 - g * p.S);
 #endif
-        const int c0 = chunk * 64 + kcl * 8;
-        const int which = (c0 < p.C[0]) ? 0 : 1;
-        const __nv_bfloat16* gbase = reinterpret_cast<const __nv_bfloat16*>(which ? src1 : src0) +
-                                     static_cast<size_t>(g) * (which ? gstride1 : gstride0) + (c0 - (which ? p.C[0] : 0));
-        const int* toff = t_off + (which ? p.S * P : 0) + s * P;
+        const __nv_bfloat16* gbase;
+        const int* toff;
+        if (chunk < p.nchunks) {
+          const int c0 = chunk * 64 + kcl * 8;
+          const int which = (c0 < p.C[0]) ? 0 : 1;
+          gbase = reinterpret_cast<const __nv_bfloat16*>(which ? src1 : src0) + static_cast<size_t>(g) * (which ? gstride1 : gstride0) +
+                  (c0 - (which ? p.C[0] : 0));
+          toff = t_off + (which ? p.S * P : 0) + s * P;
+        } else {
+          const int c0 = (chunk - p.nchunks) * 64 + kcl * 8;
+          const int which = (c0 < p.sc_C[0]) ? 0 : 1;
+          gbase = reinterpret_cast<const __nv_bfloat16*>(which ? sc1 : sc0) + static_cast<size_t>(g) * (which ? sc_gstride1 : sc_gstride0) +
+                  (c0 - (which ? p.sc_C[0] : 0));
+          toff = t_off + (2 + which) * p.S * P + s * P;
+        }
 #pragma unroll
         for (int k = 0; k < RC; ++k) {
           const int px = slice + (k << ps_log);
 #ifdef RD_ABL_XF_NOLOAD
           dst[k] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
 #else
-          if (active && px < P) dst[k] = __ldg(reinterpret_cast<const uint4*>(gbase + toff[px]));
+          if (active && px < P) {
+            if (l2_only) asm volatile("prefetch.global.L2 [%0];" ::"l"(gbase + toff[px]));
+            else dst[k] = __ldg(reinterpret_cast<const uint4*>(gbase + toff[px]));
+          }
 #endif
         }
       };
@@ -720,12 +776,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
         const bool active = owner && s < S_act;
 #endif
         int li_n = li, chunk_n = chunk + 1;
-        if (chunk_n == p.nchunks) { chunk_n = 0; ++li_n; }
-        if (PREFETCH && st + 1 < total) load_step(nxt, li_n, chunk_n);
+        if (chunk_n == steps_per_group) { chunk_n = 0; ++li_n; }
+        const bool normalise = chunk < p.nchunks;  // shortcut chunks are staged raw
+        if (st + 1 < total) load_step(nxt, li_n, chunk_n, !PREFETCH);
         // ---- statistics of this lane's pixels: (sum, sum of squares) of channels 0-3 and 4-7, then over the team
         float ca[8], cb[8];
 #ifndef RD_ABL_XF_NOSTATS
-        {
+        if (normalise) {
           float s_lo = 0.0f, q_lo = 0.0f, s_hi = 0.0f, q_hi = 0.0f;
 #pragma unroll
           for (int k = 0; k < RC; ++k) {
@@ -776,7 +833,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             const int px = slice + (k << ps_log);
             if (px < P) {
 #ifndef RD_ABL_XF_NOAPPLY
-              gn_apply(raw[k], ca, cb);
+              if (normalise) gn_apply(raw[k], ca, cb);
 #endif
               a4[trow[px]] = raw[k];
             }
@@ -1004,6 +1061,24 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   else RD_REQUIRE(op.src[0].C % 64 == 0, "conv: with two sources the first must have a multiple of 64 channels");
   RD_REQUIRE(cin % 64 == 0, "conv: total input channels (%d) must be a multiple of 64", cin);
   p.nsrc = op.nsrc;
+  // fused 1x1 shortcut (see ConvParams): raw sources gathered to the same H_in x W_in grid
+  RD_REQUIRE(op.sc_nsrc >= 0 && op.sc_nsrc <= 2, "conv: sc_nsrc must be 0, 1 or 2");
+  int sc_cin = 0;
+  for (int i = 0; i < op.sc_nsrc; ++i) {
+    RD_REQUIRE(op.sc_src[i].ptr && op.sc_src[i].C % 8 == 0 && op.sc_src[i].C > 0, "conv: shortcut source %d channels must be a multiple of 8", i);
+    RD_REQUIRE(op.sc_src[i].Hs >= 1 && op.sc_src[i].Ws >= 1 && op.sc_src[i].Hs <= MAX_HW && op.sc_src[i].Ws <= MAX_HW, "conv: bad shortcut source size");
+    p.sc_src[i] = op.sc_src[i].ptr;
+    p.sc_C[i] = op.sc_src[i].C; p.sc_Hs[i] = op.sc_src[i].Hs; p.sc_Ws[i] = op.sc_src[i].Ws;
+    nearest_map(p.sc_ymap[i], op.H_in, op.sc_src[i].Hs);
+    nearest_map(p.sc_xmap[i], op.W_in, op.sc_src[i].Ws);
+    sc_cin += op.sc_src[i].C;
+  }
+  if (op.sc_nsrc > 0) {
+    RD_REQUIRE(sc_cin % 64 == 0 && (op.sc_nsrc == 1 || op.sc_src[0].C % 64 == 0), "conv: shortcut channels must come in multiples of 64");
+    RD_REQUIRE(op.stride == 1 && !p.x3 && !op.residual, "conv: a fused shortcut needs stride 1, the bf16 plan and no residual");
+  }
+  p.sc_nsrc = op.sc_nsrc;
+  p.sc_chunks = sc_cin / 64;
   p.H = op.H_in; p.W = op.W_in;
   p.ntaps = op.ntaps;
   if (op.ntaps == 9) {
@@ -1031,7 +1106,7 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   p.out_scale = op.out_scale; p.out = op.out; p.B2 = op.B2;
   const int planes = p.x3 ? 2 : 1;  // hi + lo images of every operand in the fp32-class mode
   p.w_slab_bytes = p.N * 128 * planes;
-  p.n_slabs = p.nchunks * p.ntaps;
+  p.n_slabs = p.nchunks * p.ntaps + p.sc_chunks;
 
   // Tile geometry.  Per candidate tile count: samples per group, row efficiency, whether the TMEM
   // accumulators can be double-buffered (2*nt*N <= 512 columns) and whether the whole filter stays
@@ -1045,8 +1120,20 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   // measurement switches (read once; defaults are the shipped configuration)
   static const int wmax = [] { int w = env_int("RD_CONV_WSTAGES", 4); return w < 2 ? 2 : (w > MAX_W_STAGES ? MAX_W_STAGES : w); }();
   static const int astream = env_int("RD_CONV_ASTAGES_STREAM", 3) <= 2 ? 2 : 3;
+  // RD_CONV_FORCE_NT="cin,n,h,nt;..." pins the tile count of the launches with that (C_in, C_out, H_in) -- geometry experiments
+  int force_nt = 0;
+  {
+    static const char* spec = getenv("RD_CONV_FORCE_NT");
+    for (const char* q = spec; q && *q;) {
+      int a = 0, b = 0, c = 0, d = 0;
+      if (sscanf(q, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a == cin && b == p.N && c == op.H_in) force_nt = d;
+      q = strchr(q, ';');
+      if (q) ++q;
+    }
+  }
   for (int nt = 1; nt <= 4; ++nt) {
     if (nt * p.N > 512 || nt * 128 < p.rps) continue;
+    if (force_nt && nt != force_nt) continue;
     ConvParams c = p;
     c.n_tiles = nt;
     c.R = (nt * 128 + max_shift) | 1;
@@ -1054,8 +1141,15 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     if (op.samples_per_cta > 0 && op.samples_per_cta < c.S) c.S = op.samples_per_cta;
     c.acc_bufs = (2 * nt * p.N <= 512) ? 2 : 1;
     c.a_stage_bytes = (8 * c.R * 16 + 127) / 128 * 128 * planes;
-    c.a_stages = (p.nchunks == 1) ? 2 : 3;
+    c.a_stages = (p.nchunks + p.sc_chunks == 1) ? 2 : 3;
     c.w_resident = 1;
+    // launches with a fused shortcut have one short extra chunk per 64 shortcut channels: a resident filter with two
+    // operand stages beats a streamed filter with three (RD_CONV_SC_RES2=0 restores the generic rule)
+    static const int sc_res2 = env_int("RD_CONV_SC_RES2", 1);
+    if (sc_res2 && p.sc_chunks > 0 && c.a_stages == 3 && conv_smem_layout(c).total > smem_cap) {
+      c.a_stages = 2;
+      if (conv_smem_layout(c).total > smem_cap) c.a_stages = 3;
+    }
     if (conv_smem_layout(c).total > smem_cap) {
       // Streamed filter: the ring has to cover the L2 latency of a slab at the rate the tensor core consumes them
       // (8-16 KB per ~600 cycles), i.e. tens of KB in flight -- it gets whatever shared memory two operand stages
@@ -1078,6 +1172,7 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
       const int slots = (p.H * p.W + ps - 1) / ps;
       if (slots <= 16) { c.xmode = slots <= 4 ? 4 : (slots <= 9 ? 9 : 16); c.rc_PS = ps; }
     }
+    if (p.sc_chunks > 0 && c.xmode == 0) continue;  // the fused shortcut is staged by the team-mode transform only
     double score = static_cast<double>(c.S * valid_px) / (nt * 128);
     if (c.acc_bufs == 1) score *= 0.75;
     if (!c.w_resident) score *= (nt >= 2 ? 0.97 : 0.85);  // streamed weights are re-read per group: favour larger groups

@@ -26,7 +26,8 @@ class OpConv(C.Structure):
         ("H_out", i32), ("W_out", i32), ("ntaps", i32), ("C_out", i32), ("gn_groups", i32), ("gn_silu", i32),
         ("gn_eps", C.c_float), ("gn_gamma", vp), ("gn_beta", vp), ("w", vp), ("bias", vp), ("tproj", vp),
         ("tproj_stride", i32), ("tproj_off", i32), ("tproj_wrap", i32), ("residual", vp), ("out_scale", C.c_float), ("out", vp),
-        ("B2", i32), ("samples_per_cta", i32), ("precision", i32), ("out_stride", i32)]
+        ("B2", i32), ("samples_per_cta", i32), ("precision", i32), ("out_stride", i32),
+        ("sc_src", ConvSrc * 2), ("sc_nsrc", i32), ("_pad0", i32)]
 
 
 class OpAttn(C.Structure):

@@ -117,6 +117,13 @@ class Engine:
         if bool(weights.x3) != (self.prec == D.RD_PREC_F32X3):
             raise RuntimeError("packed weights and engine precision disagree")
         self.act_dtype = torch.float32 if self.prec == D.RD_PREC_F32X3 else torch.bfloat16
+        import os
+        self.fuse_shortcut = os.environ.get("RD_FUSE_SHORTCUT", "1") != "0"  # A/B switch (measurement)
+        # identity skips are fused (as a 1x1 with the identity matrix) at the image sizes where it measured faster than the
+        # epilogue's residual read: RD_FUSE_IDENTITY = "all" | "none" | comma-separated pixel counts
+        ident = os.environ.get("RD_FUSE_IDENTITY", "16")
+        self.fuse_identity_px = (set(range(1, 1 << 12)) if ident == "all" else set() if ident == "none"
+                                 else {int(v) for v in ident.split(",") if v})
         self.B2 = 2 * B if cfg else B
         nc = max(spec.num_classes, 1)
         dev = self.device
@@ -168,7 +175,7 @@ class Engine:
                                D.RD_OP_IN_CONV: "in_conv", D.RD_OP_OUT_HEAD: "out_head", D.RD_OP_ATTN_BLOCK: "attn_block"}[op.kind]
 
     def _conv(self, name, srcs, H_in, W_in, C_out, wname, bias, *, ntaps=9, pad=1, stride=1, gn=None, silu=1,
-              tproj_off=None, residual=None, out_scale=1.0) -> _Act:
+              tproj_off=None, residual=None, out_scale=1.0, shortcut_srcs=None) -> _Act:
         if stride == 2:
             Ho, Wo = _down_hw(H_in, W_in)
         else:
@@ -196,9 +203,15 @@ class Engine:
                 c.tproj_wrap = self.B if self.temb_rows == self.B + 1 else 0
             if residual is not None:
                 c.residual = residual.ptr + esz * n0
+            if shortcut_srcs is not None:  # raw 1x1 shortcut accumulated into the same tile (wname holds both filters)
+                c.sc_nsrc = len(shortcut_srcs)
+                for i, s in enumerate(shortcut_srcs):
+                    c.sc_src[i].ptr, c.sc_src[i].C, c.sc_src[i].Hs, c.sc_src[i].Ws = s.ptr, s.C, s.H, s.W
             c.out_scale, c.out, c.B2, c.samples_per_cta = out_scale, out.ptr + esz * n0, self.B2, 0
             self._add(op, name if si == 0 else f"{name}#s{si}")
         self.conv_flops_per_sample += 2.0 * Ho * Wo * C_out * sum(s.C for s in srcs) * ntaps
+        if shortcut_srcs is not None:
+            self.conv_flops_per_sample += 2.0 * Ho * Wo * C_out * sum(s.C for s in shortcut_srcs)
         self.tensors[name] = out
         return out
 
@@ -206,6 +219,20 @@ class Engine:
         """ResnetBlockDDPMpp (layerspp.py:198-214) as [NIN shortcut] + conv0 + conv1 launches."""
         cin = sum(s.C for s in srcs)
         rs = float(1.0 / np.sqrt(2.0)) if self.spec.skip_rescale else 1.0
+        fuse = ((p + ".Conv_1.wf") in self.w.t and self.fuse_shortcut and min(C_out // 4, 32) * 8 >= C_out
+                and all(s.C % 64 == 0 for s in srcs[:-1]) and (cin != C_out or (H * W) in self.fuse_identity_px))
+        if fuse:
+            # NIN_0 rides in Conv_1's launch: extra raw K-chunks into the same accumulator (no launch, no residual read)
+            h = self._conv(p + ".Conv_0", srcs, H, W, C_out, p + ".Conv_0.w", p + ".Conv_0.bias", gn=p + ".GroupNorm_0",
+                           tproj_off=self.w.dense_offsets[p])
+            try:
+                return self._conv(p, [h], H, W, C_out, p + ".Conv_1.wf", p + ".Conv_1.bias_f", gn=p + ".GroupNorm_1",
+                                  out_scale=rs, shortcut_srcs=srcs)
+            except RuntimeError:  # no tile geometry for the fused form at this size: separate NIN launch + residual
+                short = (self._conv(p + ".NIN_0", srcs, H, W, C_out, p + ".NIN_0.w", p + ".NIN_0.bias", ntaps=1, pad=0)
+                         if cin != C_out else srcs[0])
+                return self._conv(p, [h], H, W, C_out, p + ".Conv_1.w", p + ".Conv_1.bias", gn=p + ".GroupNorm_1",
+                                  residual=short, out_scale=rs)
         if cin != C_out:
             short = self._conv(p + ".NIN_0", srcs, H, W, C_out, p + ".NIN_0.w", p + ".NIN_0.bias", ntaps=1, pad=0)
         else:

@@ -111,6 +111,18 @@ class PackedWeights:
             if f"{p}.NIN_0.W" in sd:
                 self._put_nin(f"{p}.NIN_0", f32(sd[f"{p}.NIN_0.W"]))
                 self._put(f"{p}.NIN_0.bias", f32(sd[f"{p}.NIN_0.b"]))
+                if not self.x3 and sd[f"{p}.NIN_0.W"].shape[1] <= MAX_N_PER_LAUNCH:
+                    # fused shortcut (csrc/conv_gemm.cu): Conv_1's 3x3 slabs followed by NIN_0's 1x1 slabs, one bias
+                    self._put(f"{p}.Conv_1.wf", torch.cat([pack_conv3x3(f32(sd[f"{p}.Conv_1.weight"])).reshape(-1),
+                                                            pack_1x1(f32(sd[f"{p}.NIN_0.W"])).reshape(-1)]))
+                    self._put(f"{p}.Conv_1.bias_f", f32(sd[f"{p}.Conv_1.bias"]) + f32(sd[f"{p}.NIN_0.b"]))
+            if f"{p}.NIN_0.W" not in sd and not self.x3 and sd[f"{p}.Conv_1.weight"].shape[0] <= MAX_N_PER_LAUNCH:
+                # identity shortcut as a fused 1x1 with the identity matrix (exact in bf16): the skip connection is added
+                # by the tensor core instead of a residual read in the epilogue
+                co = sd[f"{p}.Conv_1.weight"].shape[0]
+                self._put(f"{p}.Conv_1.wf", torch.cat([pack_conv3x3(f32(sd[f"{p}.Conv_1.weight"])).reshape(-1),
+                                                        pack_1x1(torch.eye(co, device=self.device)).reshape(-1)]))
+                self._put(f"{p}.Conv_1.bias_f", f32(sd[f"{p}.Conv_1.bias"]))
             w = f32(sd[f"{p}.Dense_0.weight"])
             self.dense_offsets[p] = off
             off += w.shape[0]
