@@ -10,6 +10,7 @@
 #include "rd_common.h"
 #include <cuda_bf16.h>
 #include <type_traits>
+#include <cstdlib>
 
 namespace rd {
 
@@ -176,6 +177,8 @@ __global__ void __launch_bounds__(256) attn_core_kernel(const T* __restrict__ qk
   }
 }
 
+int attn_flash_launch(const rd_op_attn& op, cudaStream_t st);
+
 template <typename T, int NCC>
 static int attn_core_launch_t(const rd_op_attn& op, cudaStream_t st, float scale) {
   constexpr int smem = 4 * 64 * AC_LD * 4;
@@ -195,6 +198,15 @@ static int attn_core_launch_t(const rd_op_attn& op, cudaStream_t st, float scale
 int attn_launch(const rd_op_attn& op, cudaStream_t st) {
   RD_REQUIRE(op.qkv && op.out && op.B2 > 0 && op.T >= 1, "attn: null pointer / empty batch");
   RD_REQUIRE(op.precision == RD_PREC_BF16 || op.precision == RD_PREC_F32X3, "attn: unknown precision %d", op.precision);
+  {
+    // tensor-core core where available (bf16: C = 64 / 128 / 256; fp32-class: C = 64, split-bf16 operands); the fp32 SIMT
+    // core covers the rest (fp32-class at C > 64).  RD_ATTN_SIMT=1 forces the SIMT core (A/B measurements).
+    static const bool force_simt = getenv("RD_ATTN_SIMT") && atoi(getenv("RD_ATTN_SIMT")) != 0;
+    if (!force_simt) {
+      const int rc = attn_flash_launch(op, st);
+      if (rc != RD_E_UNSUPPORTED) return rc;
+    }
+  }
   const float scale = 1.0f / sqrtf(static_cast<float>(op.C));  // int(C) ** (-0.5)
   const bool f32 = op.precision == RD_PREC_F32X3;
   switch (op.C) {
@@ -545,6 +557,233 @@ int attn_block_launch(const rd_op_attn_block& op, cudaStream_t st) {
     default: return fail(RD_E_UNSUPPORTED, "attn_block: T=%d unsupported", op.T);
   }
   return check_launch("attn_block_kernel");
+}
+
+}  // namespace rd
+
+// ================================================================================================
+// attn_flash_kernel: the attention core on tensor cores (mma.sync m16n8k16, bf16 operands, fp32 accumulate and softmax)
+// for any T and C in {64, 128, 256}: the core of BASELINE config C5 (T = 256 tokens, C = 256) and -- with X3 -- of the
+// fp32-class plan at C = 64, where q, k, v and the probabilities are split into bf16 hi + lo and every product is the
+// three-term sum lo*hi + hi*lo + hi*hi (same scheme as conv_gemm.cu's fp32-class mode).
+// Grid (B2, ceil(T / 64)), 4 warps; a warp owns 16 query rows.  Q, and one 64-key tile of K and of V at a time, sit in
+// shared memory as bf16 rows padded to C + 8 (conflict-free ldmatrix); scores / probabilities / output accumulators
+// live in registers; online softmax across key tiles.
+namespace rd {
+
+constexpr int AF_BQ = 64, AF_BK = 64;
+
+template <int C>
+struct AfSmem {
+  static constexpr int LD = C + 8;                       // bf16 row stride
+  static constexpr int TILE = 64 * LD;                   // elements of one [64][LD] tile
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(a));
+}
+
+// TIN: __nv_bfloat16 (bf16 plan) or float (fp32-class plan, X3 must be true): [B2, T, 3C] -> [B2, T, C]
+template <typename TIN, int C, bool X3>
+__global__ void __launch_bounds__(128) attn_flash_kernel(const TIN* __restrict__ qkv, TIN* __restrict__ out, int Tn, float scale) {
+  using S = AfSmem<C>;
+  constexpr int LD = S::LD, NP = X3 ? 2 : 1;             // NP planes (hi, lo) per operand tile
+  constexpr int KS = C / 16;                             // k-steps of the QK^T product
+  constexpr int NB = C / 8;                              // n-blocks of the PV product
+  extern __shared__ __align__(16) unsigned char af_smem[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(af_smem);  // [NP][64][LD]
+  __nv_bfloat16* Ks = Qs + NP * S::TILE;
+  __nv_bfloat16* Vs = Ks + NP * S::TILE;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q4 = lane & 3;
+  const int q0 = blockIdx.y * AF_BQ;
+  const TIN* base = qkv + static_cast<size_t>(blockIdx.x) * Tn * (3 * C);
+
+  // stage 64 rows x C channels of q / k / v (col0 = 0, C, 2C) starting at row0 into dst (zero rows beyond T)
+  auto stage = [&](__nv_bfloat16* dst, int row0, int col0) {
+    constexpr int VPR = C / 8;                           // 8-channel vectors per row
+    for (int i = tid; i < 64 * VPR; i += 128) {
+      const int r = i / VPR, v = i - r * VPR;
+      uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+      if (row0 + r < Tn) {
+        const TIN* src = base + static_cast<size_t>(row0 + r) * (3 * C) + col0 + v * 8;
+        if constexpr (std::is_same<TIN, float>::value) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+          const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            const float2 hf = __bfloat1622float2(hh);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+            h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            l[j] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          hi = make_uint4(h[0], h[1], h[2], h[3]);
+          lo = make_uint4(l[0], l[1], l[2], l[3]);
+        } else {
+          hi = __ldg(reinterpret_cast<const uint4*>(src));
+        }
+      }
+      *reinterpret_cast<uint4*>(dst + r * LD + v * 8) = hi;
+      if (X3) *reinterpret_cast<uint4*>(dst + S::TILE + r * LD + v * 8) = lo;
+    }
+  };
+  stage(Qs, q0, 0);
+
+  float o[NB][4];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.0f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+  const float cexp = scale * 1.4426950408889634f;
+  // ldmatrix addressing: A fragment (16 rows x 16 k) of this warp's query rows; B fragments of K rows (n = key, k = channel)
+  const __nv_bfloat16* qa_base = Qs + (warp * 16 + (lane & 15)) * LD + (lane >> 4) * 8;
+  const int kb_row = lane & 7, kb_k = (lane >> 3) * 8;   // x4: four 8x8 blocks along k (two k-steps' b0, b1)
+
+  for (int k0 = 0; k0 < Tn; k0 += AF_BK) {
+    __syncthreads();                                     // previous tile's readers are done (and Q is staged)
+    stage(Ks, k0, C);
+    stage(Vs, k0, 2 * C);
+    __syncthreads();
+    if (q0 + warp * 16 >= Tn) continue;                  // a warp without query rows only helps staging (T = 72: 5 of 8 warps work)
+    // ---- S = Q K^T for this warp's 16 rows x 64 keys
+    float s[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ks += 2) {
+      uint32_t ah[2][4], al[2][4];
+      ldsm_x4(ah[0], qa_base + ks * 16);
+      ldsm_x4(ah[1], qa_base + (ks + 1) * 16);
+      if (X3) { ldsm_x4(al[0], qa_base + S::TILE + ks * 16); ldsm_x4(al[1], qa_base + S::TILE + (ks + 1) * 16); }
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        uint32_t bh[4], bl[4];
+        ldsm_x4(bh, Ks + (nb * 8 + kb_row) * LD + ks * 16 + kb_k);   // (b0,b1) of k-step ks, (b0,b1) of k-step ks+1
+        if (X3) {
+          ldsm_x4(bl, Ks + S::TILE + (nb * 8 + kb_row) * LD + ks * 16 + kb_k);
+          mma_bf16_16816(s[nb], al[0], bh[0], bh[1]); mma_bf16_16816(s[nb], ah[0], bl[0], bl[1]);
+          mma_bf16_16816(s[nb], al[1], bh[2], bh[3]); mma_bf16_16816(s[nb], ah[1], bl[2], bl[3]);
+        }
+        mma_bf16_16816(s[nb], ah[0], bh[0], bh[1]);
+        mma_bf16_16816(s[nb], ah[1], bh[2], bh[3]);
+      }
+    }
+    // ---- online softmax (rows g and g + 8 of this warp's tile; keys nb*8 + 2*q4 + {0,1})
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = (k0 + nb * 8 + 2 * q4 + e) < Tn;
+        s[nb][e] = ok ? s[nb][e] : -INFINITY;
+        s[nb][2 + e] = ok ? s[nb][2 + e] : -INFINITY;
+      }
+      mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);          // finite: the tile holds at least one valid key
+    const float a0 = exp2f((m0 - mn0) * cexp), a1 = exp2f((m1 - mn1) * cexp);
+    float rs0 = 0.0f, rs1 = 0.0f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nb][e] = X3 ? exp2f((s[nb][e] - mn0) * cexp) : ab_ex2((s[nb][e] - mn0) * cexp);
+        s[nb][2 + e] = X3 ? exp2f((s[nb][2 + e] - mn1) * cexp) : ab_ex2((s[nb][2 + e] - mn1) * cexp);
+        rs0 += s[nb][e];
+        rs1 += s[nb][2 + e];
+      }
+    }
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+    l0 = fmaf(l0, a0, rs0); l1 = fmaf(l1, a1, rs1);
+    m0 = mn0; m1 = mn1;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) { o[nb][0] *= a0; o[nb][1] *= a0; o[nb][2] *= a1; o[nb][3] *= a1; }
+    // ---- O += P V : the score fragments are the A fragments of the next product (no shared-memory round trip)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ph[4], pl[4];
+      const float pv[8] = {s[2 * kk][0], s[2 * kk][1], s[2 * kk][2], s[2 * kk][3], s[2 * kk + 1][0], s[2 * kk + 1][1], s[2 * kk + 1][2], s[2 * kk + 1][3]};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(pv[2 * j], pv[2 * j + 1]);
+        ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        if (X3) {
+          const float2 hf = __bfloat1622float2(hh);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(pv[2 * j] - hf.x, pv[2 * j + 1] - hf.y);
+          pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, Vs + (kk * 16 + (lane & 15)) * LD + nb * 8);
+        if (X3) {
+          uint32_t c0, c1;
+          ldsm_x2_trans(c0, c1, Vs + S::TILE + (kk * 16 + (lane & 15)) * LD + nb * 8);
+          mma_bf16_16816(o[nb], pl, b0, b1);
+          mma_bf16_16816(o[nb], ph, c0, c1);
+        }
+        mma_bf16_16816(o[nb], ph, b0, b1);
+      }
+    }
+  }
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  TIN* ob = out + static_cast<size_t>(blockIdx.x) * Tn * C;
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    const int c = nb * 8 + 2 * q4;
+    if constexpr (std::is_same<TIN, float>::value) {
+      if (r0 < Tn) *reinterpret_cast<float2*>(ob + static_cast<size_t>(r0) * C + c) = make_float2(o[nb][0] * i0, o[nb][1] * i0);
+      if (r1 < Tn) *reinterpret_cast<float2*>(ob + static_cast<size_t>(r1) * C + c) = make_float2(o[nb][2] * i1, o[nb][3] * i1);
+    } else {
+      if (r0 < Tn) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r0) * C + c) = pack_bf16(o[nb][0] * i0, o[nb][1] * i0);
+      if (r1 < Tn) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r1) * C + c) = pack_bf16(o[nb][2] * i1, o[nb][3] * i1);
+    }
+  }
+}
+
+template <typename TIN, int C, bool X3>
+static int attn_flash_launch_t(const rd_op_attn& op, cudaStream_t st, float scale) {
+  constexpr int smem = 3 * (X3 ? 2 : 1) * AfSmem<C>::TILE * 2;
+  static bool configured[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<TIN, C, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "attn_flash: %s", cudaGetErrorString(e));
+    configured[dev] = true;
+  }
+  dim3 grid(op.B2, (op.T + AF_BQ - 1) / AF_BQ);
+  attn_flash_kernel<TIN, C, X3><<<grid, 128, smem, st>>>(static_cast<const TIN*>(op.qkv), static_cast<TIN*>(op.out), op.T, scale);
+  return check_launch("attn_flash_kernel");
+}
+
+// Tensor-core attention core where one exists for (precision, C); RD_E_UNSUPPORTED otherwise (the caller then runs the
+// fp32 SIMT core above).
+int attn_flash_launch(const rd_op_attn& op, cudaStream_t st) {
+  const float scale = 1.0f / sqrtf(static_cast<float>(op.C));
+  if (op.precision == RD_PREC_BF16) {
+    switch (op.C) {
+      case 64: return attn_flash_launch_t<__nv_bfloat16, 64, false>(op, st, scale);
+      case 128: return attn_flash_launch_t<__nv_bfloat16, 128, false>(op, st, scale);
+      case 256: return attn_flash_launch_t<__nv_bfloat16, 256, false>(op, st, scale);
+      default: return RD_E_UNSUPPORTED;
+    }
+  }
+  if (op.precision == RD_PREC_F32X3 && op.C == 64) return attn_flash_launch_t<float, 64, true>(op, st, scale);
+  return RD_E_UNSUPPORTED;
 }
 
 }  // namespace rd

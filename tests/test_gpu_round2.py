@@ -52,7 +52,7 @@ def test_fp32_mode_forward_vs_reference(tag, isz):
     taps = {k[4:]: rel_to_max(eng.activation(k[4:]).cpu(), torch.from_numpy(g[k])) for k in g.files
             if k.startswith("tap:") and k[4:] in eng.tensors}
     print(f"fp32-mode forward {tag}: rel-to-max err {err:.3e}; worst tap {max(taps, key=taps.get)} {max(taps.values()):.3e}")
-    assert err <= 1e-4 and max(taps.values()) <= 1e-4
+    assert err <= 3e-5 and max(taps.values()) <= 3.5e-5      # measured 1.9e-5 / 2.5e-5 (profiles/r02b_pytest_round2.log)
     # guided score through the drop-in wrappers, per-sample guidance weights up to 4
     sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=1000)
     t, w = torch.from_numpy(g["t_cfg"]).to(DEV), torch.from_numpy(g["w_cfg"]).to(DEV)
@@ -60,7 +60,7 @@ def test_fp32_mode_forward_vs_reference(tag, isz):
         s = mutils.get_cf_score_fn(sde, model, labels, w)(x, t)
     e = rel_to_max(s.cpu(), torch.from_numpy(g["score_cfg"]))
     print(f"fp32-mode guided score {tag}: rel-to-max err {e:.3e}")
-    assert e <= 3e-4
+    assert e <= 8e-5                                          # measured 5.8e-5 (guidance weights up to 4 amplify by 1 + 2w)
 
 
 @pytest.mark.parametrize("tag,corrector", [("pc_N200", "langevin"), ("pc_N1000", "langevin"), ("pred_only_N1000", "none")])
@@ -78,7 +78,10 @@ def test_fp32_mode_sampler_vs_reference(tag, corrector):
     assert bool(cube.inside(xg).all())
     d = (xg.cpu() - torch.from_numpy(g["x_final"])).abs()
     print(f"fp32-mode sampler {tag}: max {float(d.max()):.3e} mean {float(d.mean()):.3e}  (north_star fp32 mode: 1e-5)")
-    assert float(d.max()) <= 1e-3 and float(d.mean()) <= 1e-4
+    # measured (profiles/r02b_pytest_round2.log) x 1.5; the reference's own sensitivity to a 1e-6 perturbation of x0 on this
+    # kind of model is 4e-5 max / 7e-6 mean at N = 1000 with the corrector, 6e-6 / 1e-6 without
+    bar = {"pc_N200": (1.0e-4, 3.2e-5), "pc_N1000": (2.8e-4, 7.7e-5), "pred_only_N1000": (2.4e-5, 5.7e-6)}[tag]
+    assert float(d.max()) <= bar[0] and float(d.mean()) <= bar[1]
 
 
 # ------------------------------------------------------------------------------------------------ bf16 plan, N = 1000
@@ -137,9 +140,9 @@ def test_multi_step_corrector_native(precision):
     print(f"{precision} n_steps_each=2: native vs reference max {float(d.max()):.3e} mean {float(d.mean()):.3e}; "
           f"native vs generic loop max {float(dl.max()):.3e}")
     if precision == "fp32":
-        assert float(d.max()) <= 1e-3 and float(d.mean()) <= 1e-4
+        assert float(d.max()) <= 3e-4 and float(d.mean()) <= 7.5e-5   # measured 2.0e-4 / 4.9e-5
     else:
-        assert float(d.mean()) <= 3e-2
+        assert float(d.mean()) <= 1.5e-2 and float(d.max()) <= 5.5e-2  # measured 9.7e-3 / 3.6e-2 (bf16 band, N = 40)
 
 
 # ------------------------------------------------------------------------------------------------ scale_by_sigma
@@ -155,7 +158,7 @@ def test_scale_by_sigma(precision):
     ref = torch.from_numpy(g["y"])
     per_sample = ((y.cpu() - ref).abs().amax(dim=(1, 2, 3)) / ref.abs().amax(dim=(1, 2, 3)))
     print(f"{precision} scale_by_sigma forward: per-sample rel-to-max err {per_sample.tolist()}")
-    assert float(per_sample.max()) <= (1e-4 if precision == "fp32" else 3e-2)
+    assert float(per_sample.max()) <= (5e-6 if precision == "fp32" else 3e-3)   # measured 2.0e-6 / 1.7e-3
     gs = load_golden("sampler_pc_N30_sbs.npz")
     N, B, w = int(gs["N"]), int(gs["B"]), float(gs["w"])
     sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=N)
@@ -170,8 +173,8 @@ def test_scale_by_sigma(precision):
     print(f"{precision} scale_by_sigma sampler N30: native vs reference max {float(d.max()):.3e} mean {float(d.mean()):.3e}; "
           f"native vs generic loop max {float((xn - xl).abs().max()):.3e}")
     assert bool(cube.inside(xn).all())
-    assert float(d.mean()) <= (1e-4 if precision == "fp32" else 5e-2)
-    assert float((xn - xl).abs().mean()) <= (1e-4 if precision == "fp32" else 5e-2)
+    assert float(d.mean()) <= (1.5e-6 if precision == "fp32" else 7e-4)          # measured 4.7e-7 / 3.4e-4
+    assert float((xn - xl).abs().max()) <= (8e-6 if precision == "fp32" else 4e-3)  # measured 2.6e-6 / 1.5e-3
 
 
 # ------------------------------------------------------------------------------------------------ BASELINE config C5
@@ -194,8 +197,8 @@ def test_c5_forward_vs_reference(precision):
     taps = {k[4:]: rel_to_max(eng.activation(k[4:]).cpu(), torch.from_numpy(g[k])) for k in g.files
             if k.startswith("tap:") and k[4:] in eng.tensors}
     print(f"{precision} C5 forward: rel-to-max err {err:.3e}; taps " + ", ".join(f"{k} {v:.2e}" for k, v in taps.items()))
-    assert err <= (2e-4 if precision == "fp32" else 4e-2)
-    assert max(taps.values()) <= (2e-4 if precision == "fp32" else 4e-2)
+    assert err <= (3e-5 if precision == "fp32" else 1.4e-2)                 # measured 1.8e-5 / 9.3e-3
+    assert max(taps.values()) <= (7e-5 if precision == "fp32" else 1.6e-2)  # measured 4.6e-5 / 1.1e-2
 
 
 # ------------------------------------------------------------------------------------------------ weight swaps
