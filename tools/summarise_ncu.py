@@ -1,11 +1,11 @@
 """Turn gpurun_out/ ncu artefacts into the small tracked summaries under profiles/.
-usage: python tools/summarise_ncu.py <tag> [launches.csv] [report.ncu-rep]"""
+usage: python tools/summarise_ncu.py <tag> [launches.csv] [report.ncu-rep ...]"""
 import collections, csv, io, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 launches = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "launches.csv")
-rep = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "prof_conv.ncu-rep")
-out = os.path.join(ROOT, "profiles")
+reps = sys.argv[3:] if len(sys.argv) > 3 else [os.path.join(ROOT, "gpurun_out", "prof_conv.ncu-rep")]
+out = os.environ.get("RD_SUMMARY_OUT", os.path.join(ROOT, "profiles"))
 os.makedirs(out, exist_ok=True)
 if os.path.exists(launches):
     lines = [l for l in open(launches) if not l.startswith("==")]
@@ -23,19 +23,20 @@ if os.path.exists(launches):
         f.write("total %.1f us over %d launches\n" % (tot, sum(n for n, _ in agg.values())))
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%-70s n=%4d total %10.1f us avg %8.1f us share %.4f\n" % (k[:70], n, t, t / n, t / tot))
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    r = list(csv.reader(io.StringIO(raw)))
-    hdr, units, rows = r[0], r[1], r[2:]
-    keep = re.compile(r"Kernel Name|gpu__time_duration.sum|dram__bytes_(read|write).sum$|dram__cycles_active.avg.pct|gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed|"
-                      r"sm__pipe_tensor_cycles_active|sm__warps_active.avg.pct|launch__registers_per_thread|launch__grid_size|launch__block_size|"
-                      r"launch__shared_mem_per_block_dynamic|launch__occupancy_limit|sm__throughput.avg.pct_of_peak_sustained_elapsed|smsp__issue_active.avg.pct|"
-                      r"smsp__pcsamp_warps_issue_stalled_[a-z_]+$|lts__t_sector_hit_rate.pct|l1tex__t_sector_hit_rate.pct|sm__inst_executed_pipe_uniform|smsp__inst_executed.sum$")
-    with open(os.path.join(out, f"{tag}_{os.path.basename(rep).replace('.ncu-rep','')}_ncu_summary.txt"), "w") as f:
-        f.write("ncu --set full --clock-control none --import-source on  (%s)\n" % os.path.basename(rep))
-        for i, h in enumerate(hdr):
-            if keep.search(h) and not h.endswith("_not_issued"):
-                f.write("%-78s %-16s %s\n" % (h, units[i], " ; ".join(row[i][:28] for row in rows)))
+for rep in reps:
+  if os.path.exists(rep):
+      raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+      r = list(csv.reader(io.StringIO(raw)))
+      hdr, units, rows = r[0], r[1], r[2:]
+      keep = re.compile(r"Kernel Name|gpu__time_duration.sum|dram__bytes_(read|write).sum$|dram__cycles_active.avg.pct|gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed|"
+                        r"sm__pipe_tensor_cycles_active|sm__warps_active.avg.pct|launch__registers_per_thread|launch__grid_size|launch__block_size|"
+                        r"launch__shared_mem_per_block_dynamic|launch__occupancy_limit|sm__throughput.avg.pct_of_peak_sustained_elapsed|smsp__issue_active.avg.pct|"
+                        r"smsp__pcsamp_warps_issue_stalled_[a-z_]+$|lts__t_sector_hit_rate.pct|l1tex__t_sector_hit_rate.pct|sm__inst_executed_pipe_uniform|smsp__inst_executed.sum$")
+      with open(os.path.join(out, f"{tag}_{os.path.basename(rep).replace('.ncu-rep','')}_ncu_summary.txt"), "w") as f:
+          f.write("ncu --set full --clock-control none --import-source on  (%s)\n" % os.path.basename(rep))
+          for i, h in enumerate(hdr):
+              if keep.search(h) and not h.endswith("_not_issued"):
+                  f.write("%-78s %-16s %s\n" % (h, units[i], " ; ".join(row[i][:28] for row in rows)))
 traffic = os.path.join(ROOT, "gpurun_out", "conv_traffic.csv")
 if os.path.exists(traffic):
     import json
@@ -53,7 +54,13 @@ if os.path.exists(traffic):
     rd = sum(d.get("dram__bytes_read.sum", 0.0) for d in per.values())
     wr = sum(d.get("dram__bytes_write.sum", 0.0) for d in per.values())
     us = sum(d.get("gpu__time_duration.sum", 0.0) for d in per.values())
-    js = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_gemm -c 96 python tools/prof_target.py",
+    import hashlib
+    h = hashlib.sha256()
+    for fn in ("conv_gemm.cu", "rd_ptx.cuh"):
+        with open(os.path.join(ROOT, "optimized-diffusion-model_b200", "csrc", fn), "rb") as fh:
+            h.update(fh.read())
+    js = {"kernel_source_sha": h.hexdigest()[:16],   # bench.py reports this capture only for these exact kernel sources
+          "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_gemm -c 96 python tools/prof_target.py",
           "note": "per-launch averages over the conv_gemm launches of two guided forwards at 2B=16384; outputs mostly stay in the 126 MB L2 for the next layer, so writes are far below the algorithmic bytes",
           "launches": n, "dram_read_bytes_per_launch": rd / max(n, 1), "dram_write_bytes_per_launch": wr / max(n, 1),
           "dram_bytes_per_launch": (rd + wr) / max(n, 1), "ncu_us_per_launch": us / max(n, 1)}
