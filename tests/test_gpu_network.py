@@ -57,7 +57,9 @@ def test_forward_and_layer_taps_vs_reference(tag, isz):
     floor, _ = autocast_floor(ocfg, sd, x, sigma, labels)
     err = rel_to_max(y.cpu(), torch.from_numpy(g["y"]))
     print(f"forward {tag}: rel-to-max err {err:.3e} (torch bf16-autocast floor {floor:.3e})")
-    assert err <= max(1.5 * floor, 5e-3) and err <= 3e-2
+    # measured 1.14e-2 (8x9) / 1.01e-2 (9x9) against PyTorch's own bf16 autocast at 1.39e-2 / 1.19e-2
+    # (profiles/r02_pytest_gpu.log): the bf16 plan must not be worse than the framework's bf16, and stays under 1.5e-2
+    assert err <= 1.05 * floor and err <= 1.5e-2
     eng = list(model._rd_forward_engines.values())[0]
     for k in g.files:
         if k.startswith("tap:") and k[4:] in eng.tensors:
@@ -69,7 +71,9 @@ def test_forward_and_layer_taps_vs_reference(tag, isz):
     with torch.no_grad():
         s = mutils.get_cf_score_fn(sde, model, labels, w)(x, t)
     # guidance weights up to 4 amplify the bf16 score error by (1 + 2w)
-    assert rel_to_max(s.cpu(), torch.from_numpy(g["score_cfg"])) <= 1e-1
+    es = rel_to_max(s.cpu(), torch.from_numpy(g["score_cfg"]))
+    print(f"guided score {tag}: rel-to-max err {es:.3e}")
+    assert es <= 6e-2
 
 
 def test_forward_batch_sizes_and_weight_swap():
@@ -131,8 +135,9 @@ def test_sampler_tape_parity(tag, corrector):
     floor_max, floor_mean = float((xb - xo).abs().max()), float((xb - xo).abs().mean())
     d = (xg - ref).abs()
     print(f"sampler {tag}: max {float(d.max()):.3e} mean {float(d.mean()):.3e} | torch bf16 floor max {floor_max:.3e} mean {floor_mean:.3e}")
-    assert float(d.mean()) <= 1.5 * floor_mean + 1e-4
-    assert float(d.max()) <= 2.0 * floor_max + 1e-3
+    # measured 0.85-0.9 x the floor's mean and 0.53-0.88 x its max on the three tapes (profiles/r02_pytest_gpu.log)
+    assert float(d.mean()) <= 1.1 * floor_mean + 1e-4
+    assert float(d.max()) <= 1.1 * floor_max + 1e-3
     # P2: teacher-forced single iterations from the oracle's own trajectory
     eng = list(model._rd_sampler_engines.values())[-1]
     errs = []

@@ -80,7 +80,7 @@ def test_fp32_mode_sampler_vs_reference(tag, corrector):
     print(f"fp32-mode sampler {tag}: max {float(d.max()):.3e} mean {float(d.mean()):.3e}  (north_star fp32 mode: 1e-5)")
     # measured (profiles/r02b_pytest_round2.log) x 1.5; the reference's own sensitivity to a 1e-6 perturbation of x0 on this
     # kind of model is 4e-5 max / 7e-6 mean at N = 1000 with the corrector, 6e-6 / 1e-6 without
-    bar = {"pc_N200": (1.0e-4, 3.2e-5), "pc_N1000": (2.8e-4, 7.7e-5), "pred_only_N1000": (2.4e-5, 5.7e-6)}[tag]
+    bar = {"pc_N200": (1.0e-4, 3.2e-5), "pc_N1000": (2.8e-4, 7.7e-5), "pred_only_N1000": (3.0e-5, 5.9e-6)}[tag]
     assert float(d.max()) <= bar[0] and float(d.mean()) <= bar[1]
 
 
@@ -112,8 +112,8 @@ def test_bf16_sampler_N1000_vs_reference(tag, corrector):
     d = (xg - ref).abs()
     print(f"bf16 sampler {tag}: max {float(d.max()):.3e} mean {float(d.mean()):.3e} | torch bf16-autocast floor max "
           f"{float(fl.max()):.3e} mean {float(fl.mean()):.3e}  (north_star bf16: 1e-3)")
-    assert float(d.mean()) <= 1.5 * float(fl.mean()) + 1e-4
-    assert float(d.max()) <= 2.0 * float(fl.max()) + 1e-3
+    assert float(d.mean()) <= 1.1 * float(fl.mean()) + 1e-4     # measured 0.87-0.94 x the floor (profiles/r02_pytest_gpu.log)
+    assert float(d.max()) <= 1.1 * float(fl.max()) + 1e-3
 
 
 # ------------------------------------------------------------------------------------------------ multi-step corrector
