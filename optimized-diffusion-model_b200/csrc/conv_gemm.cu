@@ -1139,6 +1139,9 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     c.R = (nt * 128 + max_shift) | 1;
     c.S = (nt * 128) / p.rps;
     if (op.samples_per_cta > 0 && op.samples_per_cta < c.S) c.S = op.samples_per_cta;
+    // the per-group (bias + temb) table is S x N floats, double-buffered: keep it within 32 KB (only reached at 1x1 / 2x2
+    // images with an un-padded 1x1 filter, where a 128-row tile could hold 32-128 samples)
+    if (c.S > 4096 / p.N) c.S = 4096 / p.N > 0 ? 4096 / p.N : 1;
     c.acc_bufs = (2 * nt * p.N <= 512) ? 2 : 1;
     c.a_stage_bytes = (8 * c.R * 16 + 127) / 128 * 128 * planes;
     c.a_stages = (p.nchunks + p.sc_chunks == 1) ? 2 : 3;

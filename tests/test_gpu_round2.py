@@ -279,3 +279,46 @@ def test_attnblock_forward_standalone():
         assert e <= 1.5e-2
     with pytest.raises(NotImplementedError):
         layerspp.AttnBlockpp(128).to(DEV)(torch.randn(1, 128, 8, 9, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------ other latent shapes
+@pytest.mark.parametrize("H,W,attn", [(8, 8, 8), (12, 10, 12), (16, 16, 16), (6, 7, 0), (4, 4, 4)])
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_forward_other_latent_shapes(H, W, attn, precision):
+    """Every shipped consumer of the reference builds a SQUARE sampling shape from image_size alone (run_train.py:124-127,
+    Benchmark/gto_halo_benchmarking.py:201-206), so (B,1,8,8) is what an unmodified caller passes; other sizes exercise the
+    tile-geometry chooser, the ragged nearest-neighbour fix-up (ncsnpp.py:319-320: 12x10 -> 6x5 -> 3x3 -> 6x6 -> 6x5), the
+    fused shortcut at other pixel counts and the attention paths (fused block T <= 128, flash core T = 256)."""
+    cfg = make_config(H, attn, W=W, precision=precision)
+    ocfg = oracle_cfg(H, attn)
+    sd = O.synth_state_dict(ocfg, seed=13)
+    model = mutils.create_model(cfg).to(DEV)
+    model.load_state_dict(sd)
+    model.eval()
+    sdg = {k: v.to(DEV) for k, v in sd.items()}
+    gen = torch.Generator().manual_seed(H * 100 + W)
+    for B in (3, 37):
+        x = torch.rand(B, 1, H, W, generator=gen).to(DEV)
+        sigma = torch.exp(torch.rand(B, generator=gen) * 6.2 - 4.6).to(DEV)
+        labels = torch.rand(B, 1, generator=gen).to(DEV)
+        with torch.no_grad():
+            y = model(x, sigma, class_labels=labels)
+            ref = O.ncsnpp_forward(x, sigma, labels, sdg, ocfg)
+        e = rel_to_max(y, ref)
+        print(f"{precision} forward {H}x{W} attn@{attn} B={B}: rel-to-max err {e:.3e}")
+        assert e <= (5e-5 if precision == "fp32" else 2e-2), (H, W, B, e)
+    # a short native sampler run stays inside the cube and matches the oracle on an injected tape
+    N, B = 12, 5
+    sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=N)
+    x0, noise = O.make_tape(B, (1, H, W), (N - 1) * 2, seed=3)
+    lab = torch.rand(B, 1, generator=gen).to(DEV)
+    fn = sampling.get_sampling_fn(cfg, sde, (B, 1, H, W), 1e-5, DEV)
+    with patched(torch, "rand", lambda *a, **k: x0.clone()):
+        xs, _ = fn(model, weight=1.5, class_labels=lab, rd_tape=noise.to(DEV))
+    with torch.no_grad():
+        xo = O.pc_sampler(lambda xx, sg: O.guided_score(xx, sg, lab, 1.5, sdg, ocfg), O.VESchedule(0.01, 5.0, N, 1.0, 1e-5),
+                          O.SamplerConfig(), x0.to(DEV), noise.to(DEV))
+    d = (xs - xo).abs()
+    print(f"{precision} sampler {H}x{W} N={N}: max {float(d.max()):.3e} mean {float(d.mean()):.3e}")
+    assert bool(cube.inside(xs).all())
+    assert float(d.mean()) <= (2e-4 if precision == "fp32" else 8e-2)   # (12 coarse steps: the bf16 band is wide, cf. pc_N30)
