@@ -196,3 +196,78 @@ def test_bench_reference_arm_prints_one_json_line():
     # build container and every snapshot shipped from it), "port" = the oracle restatement when it did not travel
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] in ("reference", "port") and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+# ------------------------------------------------------------------------------------------------ round-2 host logic (CPU)
+def test_split_bf16_packing_and_channel_slices():
+    """fp32-class plan: every packed filter is a bf16 hi plane + a bf16 lo plane with hi + lo == w to 2^-16 of |w| (two
+    round-to-nearest bf16 steps); layers wider than 128 output channels are stored as 128-wide slices."""
+    import torch
+    from rdb200 import pack
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(192, 128, 3, 3, generator=g) * 0.05
+    p1, p3 = pack.pack_conv3x3(w), pack.pack_conv3x3(w, x3=True)
+    assert p1.shape == (2, 9, 8, 192, 8) and p3.shape == (2, 9, 2, 8, 192, 8) and p3.dtype == torch.bfloat16
+    assert torch.equal(p3[:, :, 0], p1)
+    rec = p3[:, :, 0].float() + p3[:, :, 1].float()
+    # un-pack: [chunk, tap, kc, n, j] -> [n, chunk*64 + kc*8 + j, tap]
+    back = rec.permute(3, 0, 2, 4, 1).reshape(192, 128, 9).reshape(192, 128, 3, 3)
+    assert float((back - w).abs().max()) <= 2.0 ** -16 * float(w.abs().max())
+    assert pack.n_slices(64) == [(0, 64)] and pack.n_slices(192) == [(0, 128), (128, 64)] and pack.n_slices(512)[-1] == (384, 128)
+    W = torch.randn(256, 128, generator=g)
+    assert pack.pack_1x1(W).shape == (4, 1, 8, 128, 8) and pack.pack_1x1(W, x3=True).shape == (4, 1, 2, 8, 128, 8)
+
+
+def test_precision_selection_and_errors(monkeypatch):
+    from rdb200 import engine
+    cfg = __import__("helpers").make_config()
+    assert engine.precision_from_config(cfg) == "bf16"
+    cfg.model.rd_precision = "fp32"
+    assert engine.precision_from_config(cfg) == "fp32" and engine.spec_from_config(cfg).precision == "fp32"
+    monkeypatch.setenv("RDB200_PRECISION", "bf16")      # the environment overrides the config (unmodified consumer scripts)
+    assert engine.precision_from_config(cfg) == "bf16"
+    monkeypatch.setenv("RDB200_PRECISION", "fp16")
+    with pytest.raises(ValueError):
+        engine.precision_from_config(cfg)
+
+
+def test_device_rk45_tables_match_scipy():
+    """The device-side solver must be scipy's RK45: same Butcher tableau, error weights and control constants
+    (scipy.integrate._ivp.rk)."""
+    from scipy.integrate._ivp import rk
+    from rdb200 import ode
+    assert np.array_equal(ode.C_NODES, rk.RK45.C) and np.array_equal(ode.B_ROW, rk.RK45.B) and np.array_equal(ode.E_ROW, rk.RK45.E)
+    for s, row in enumerate(ode.A_ROWS):
+        assert np.array_equal(row, rk.RK45.A[s][:s]), s
+    assert (ode.SAFETY, ode.MIN_FACTOR, ode.MAX_FACTOR) == (rk.SAFETY, rk.MIN_FACTOR, rk.MAX_FACTOR)
+    assert ode.ERROR_ESTIMATOR_ORDER == rk.RK45.error_estimator_order and rk.RK45.n_stages == 6
+
+
+def test_reference_copy_recipe_and_shared_bench_config():
+    """oracle/fetch_ref.py keeps a byte-for-byte, sha-stamped copy of the reference's hot-path sources outside the history
+    (when /root/reference exists, i.e. in the build container); both bench arms print the same `config` object."""
+    import importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from oracle import fetch_ref
+    if os.path.isdir(fetch_ref.SRC):
+        assert fetch_ref.fetch() and fetch_ref.available() and fetch_ref.verify()
+        with open(os.path.join(fetch_ref.DST, "cube.py"), "rb") as a, open(os.path.join(fetch_ref.SRC, "cube.py"), "rb") as b:
+            assert a.read() == b.read()
+        ign = open(os.path.join(root, ".gitignore")).read()
+        assert "oracle/_ref/" in ign
+    bench = importlib.import_module("bench")
+    a, b = bench.static_config(8192, 1), bench.static_config(8192, 1)
+    assert a == b and set(a) == {"workload", "batch_per_gpu", "global_batch", "step", "l2", "parallelism"}
+
+
+def test_checksum_segment_table_layout():
+    """rdb200.ops.checksum_segments: (address, first flat index, count) rows of at most 65536 elements covering every
+    tensor exactly once, in order (the table csrc/weights.cu walks)."""
+    import torch
+    from rdb200 import ops
+    ts = [torch.zeros(100000), torch.zeros(7), torch.zeros(65536)]
+    segs, out = ops.checksum_segments(ts)
+    rows = segs.tolist()
+    assert [r[2] for r in rows] == [65536, 100000 - 65536, 7, 65536]
+    assert [r[1] for r in rows] == [0, 65536, 100000, 100007]
+    assert rows[1][0] == ts[0].data_ptr() + 4 * 65536 and rows[2][0] == ts[1].data_ptr() and out.dtype == torch.int64
