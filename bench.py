@@ -79,7 +79,7 @@ def model_config(corrector="langevin"):
     m = types.SimpleNamespace(
         name="ncsnpp", channels=1, image_size=CONFIG["H"], image_width=CONFIG["W"], num_classes=1, cond_drop_prob=0.5,
         conditional=True, init_scale=0.0, ema_rate=0.999, nf=C5["nf"] if c5 else 64, ch_mult=C5["ch_mult"] if c5 else [1, 2, 2],
-        num_res_blocks=2, attn_resolutions=C5["attn"] if c5 else [8],
+        num_res_blocks=2, attn_resolutions=C5["attn"] if c5 else [CONFIG["H"]],
         resamp_with_conv=True, embedding_type="fourier", fourier_scale=16, skip_rescale=True, nonlinearity="swish",
         fir=False, fir_kernel=[1, 3, 3, 1], dropout=0.2, scale_by_sigma=False)
     s = types.SimpleNamespace(method="pc", predictor="euler_maruyama", corrector=corrector, denoiser="none", snr=0.01,

@@ -6,6 +6,9 @@ import torch, bench, sde_lib
 from models import utils as mutils
 bench.use_config(os.environ.get("RD_PROF_CFG", "c3"))
 H, W = bench.CONFIG["H"], bench.CONFIG["W"]
+if os.environ.get("RD_PROF_HW"):   # e.g. RD_PROF_HW=9x9: the shape every shipped artefact of the reference uses
+    H, W = (int(v) for v in os.environ["RD_PROF_HW"].split("x"))
+    bench.CONFIG.update(H=H, W=W)
 B = int(os.environ.get("RD_PROF_B", "2048" if bench.CONFIG["name"] == "c5" else "8192"))
 dev = torch.device("cuda", 0)
 model = mutils.create_model(bench.model_config()).to(dev).eval()
