@@ -322,3 +322,71 @@ def test_forward_other_latent_shapes(H, W, attn, precision):
     print(f"{precision} sampler {H}x{W} N={N}: max {float(d.max()):.3e} mean {float(d.mean()):.3e}")
     assert bool(cube.inside(xs).all())
     assert float(d.mean()) <= (2e-4 if precision == "fp32" else 8e-2)   # (12 coarse steps: the bf16 band is wide, cf. pc_N30)
+
+
+# ------------------------------------------------------------------------------------------------ the reference's own consumer
+def test_reference_consumer_runs_unmodified_on_the_b200_package():
+    """Drop-in at the level the reference is actually used: its benchmark driver (Benchmark/gto_halo_benchmarking.py,
+    the UNMODIFIED file from oracle/_ref) imports `sampling`, `sde_lib`, `utils`, `losses`, `models.utils`, `models.ema` by
+    bare name -- here they resolve to the B200 package -- and its `GTOHaloBenchmarker.generate_samples` runs the EMA swap,
+    the sampler closure (square 9x9 shape built from image_size alone) and its own un-normalisation on our samples."""
+    import os
+    import sys
+    import types
+    from oracle import fetch_ref
+    bench_dir = os.path.normpath(os.path.join(fetch_ref.DST, "..", "Benchmark"))
+    if not (fetch_ref.available() and os.path.exists(os.path.join(bench_dir, "gto_halo_benchmarking.py"))):
+        pytest.skip("oracle/_ref (copy of the unmodified reference) did not travel")
+    for name in ("matplotlib", "matplotlib.pyplot", "omegaconf", "seaborn", "pydylan", "torchvision", "torchvision.transforms",
+                 "torchvision.datasets", "PIL"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                m = types.ModuleType(name)
+                m.OmegaConf = object
+                sys.modules[name] = m
+    sys.path.append(bench_dir)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        import gto_halo_benchmarking as gb
+    assert gb.sampling is sampling and gb.sde_lib is sde_lib and gb.mutils is mutils, "the consumer must bind the B200 modules"
+    from models.ema import ExponentialMovingAverage
+    from rdb200 import codec
+    cfg, ocfg, sd, model = build(9, 9)
+    ema = ExponentialMovingAverage(model.parameters(), decay=0.999)
+    with torch.no_grad():
+        for s_ in ema.shadow_params:
+            s_.mul_(1.01)                      # the EMA weights differ from the live ones: copy_to must reach the kernels
+    before = [p.detach().clone() for p in model.parameters()]
+    N, bs = 20, 4
+    sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=N)
+    real_fn = sampling.get_sampling_fn(cfg, sde, (bs, 1, cfg.model.image_size, cfg.model.image_size), 1e-5, DEV)
+    latents, tokens = [], []
+
+    def recording_fn(score_model, **kw):
+        tokens.append(score_model._rd_weights_token())   # parameters as the sampler sees them (EMA copied in)
+        x, n = real_fn(score_model, **kw)
+        latents.append(x.clone())
+        return x, n
+
+    b = object.__new__(gb.GTOHaloBenchmarker)
+    b.config = types.SimpleNamespace(num_samples=2 * bs, batch_size=bs, guidance_weight=1.5)
+    b.device, b.score_model, b.ema, b.sampling_fn = DEV, model, ema, recording_fn
+    b.total_spherical_clips, b.total_spherical_elements = 0, 0
+    live_token = model._rd_weights_token()
+    with contextlib.redirect_stdout(io.StringIO()):
+        phys, times = b.generate_samples()
+    assert phys.shape == (2 * bs, 67) and np.isfinite(phys).all() and len(times) == 2
+    assert all(t != live_token for t in tokens), "sampling must have run on the EMA weights"
+    assert all(torch.equal(p, q) for p, q in zip(model.parameters(), before)), "ema.restore must put the live weights back"
+    lat = torch.cat(latents, 0)
+    assert bool(cube.inside(lat).all())
+    ours = codec.gto_halo_decode(lat).cpu().numpy()
+    d = np.abs(ours - phys)
+    ang = np.zeros(67, bool)
+    ang[4:64:3] = True
+    ang[5:64:3] = True
+    d[:, ang] = np.minimum(d[:, ang], np.abs(d[:, ang] - 2 * np.pi))
+    assert float(d.max()) <= 2e-5 * max(1.0, float(np.abs(phys).max())), float(d.max())
