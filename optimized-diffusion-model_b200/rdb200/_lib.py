@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from typing import Optional
 
 import torch
@@ -79,8 +80,28 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError if the .so lacks a declared symbol
             fn.restype = res
             fn.argtypes = args
+            if args and args[-1] is c_vp and name not in ("rd_plan_add", "rd_plan_create"):
+                setattr(handle, name, _device_guarded(fn))   # entry points that launch on a stream
         _lib = handle
     return _lib
+
+
+_tls = threading.local()
+
+
+def _device_guarded(fn):
+    """CUDA launches go to the calling thread's CURRENT device; the stream argument names the device the caller means.
+    `stream_ptr(device)` (evaluated for the call's last argument) leaves that device in a thread-local, and the call
+    runs under `torch.cuda.device(it)` when it is not the current one -- so one process may drive several GPUs (the
+    library keeps its launch state per device ordinal)."""
+    def call(*args):
+        dev = getattr(_tls, "device", None)   # device of this thread's most recent stream_ptr() (callers may reuse the pointer)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args)
+        with torch.cuda.device(dev):
+            return fn(*args)
+    call.__name__ = getattr(fn, "__name__", "rd_call")
+    return call
 
 
 def check(rc: int, what: str = "") -> None:
@@ -90,6 +111,9 @@ def check(rc: int, what: str = "") -> None:
 
 
 def stream_ptr(device=None) -> int:
+    if device is not None:
+        device = torch.device(device)
+        _tls.device = device if device.type == "cuda" else None
     return torch.cuda.current_stream(device).cuda_stream
 
 

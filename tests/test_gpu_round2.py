@@ -390,3 +390,31 @@ def test_reference_consumer_runs_unmodified_on_the_b200_package():
     ang[5:64:3] = True
     d[:, ang] = np.minimum(d[:, ang], np.abs(d[:, ang] - 2 * np.pi))
     assert float(d.max()) <= 2e-5 * max(1.0, float(np.abs(phys).max())), float(d.max())
+
+
+# ------------------------------------------------------------------------------------------------ several GPUs, one process
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_devices_in_one_process():
+    """The library keeps its launch state (shared-memory opt-ins, SM counts) per device ordinal and every stream call
+    runs under the device its stream belongs to: a process that uses cuda:0 and then cuda:1 gets the same numbers."""
+    cfg = make_config(8, 8)
+    ocfg = oracle_cfg(8, 8)
+    sd = O.synth_state_dict(ocfg, seed=7)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.rand(9, 1, 8, 9, generator=gen)
+    sigma = torch.exp(torch.rand(9, generator=gen) * 6.2 - 4.6)
+    labels = torch.rand(9, 1, generator=gen)
+    outs = []
+    for d in ("cuda:0", "cuda:1", "cuda:0"):
+        model = mutils.create_model(cfg).to(d)
+        model.load_state_dict(sd)
+        model.eval()
+        with torch.no_grad():
+            outs.append(model(x.to(d), sigma.to(d), class_labels=labels.to(d)).cpu())
+            r = cube.reflect((x * 3 - 1).to(d))
+            assert r.device == torch.device(d) and torch.equal(r.cpu(), O.reflect(x * 3 - 1))
+        sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=10)
+        fn = sampling.get_sampling_fn(cfg, sde, (9, 1, 8, 9), 1e-5, d)
+        xs, _ = fn(model, weight=1.5, class_labels=labels.to(d), rd_seed=4)
+        assert xs.device == torch.device(d) and bool(cube.inside(xs).all())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
