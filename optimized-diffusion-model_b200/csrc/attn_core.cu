@@ -520,12 +520,22 @@ __global__ void __launch_bounds__(32 * T16 * AB_G, (T16 <= 5 ? 2 : 1)) attn_bloc
   }
 }
 
+int attn_block_tc_launch(const rd_op_attn_block& op, cudaStream_t st);  // attn_tc.cu
+
 int attn_block_launch(const rd_op_attn_block& op, cudaStream_t st) {
   RD_REQUIRE(op.x && op.out && op.wqkv_t && op.wproj_t && op.bqkv && op.bproj && op.gamma && op.beta && op.B2 > 0,
              "attn_block: null pointer / empty batch");
   RD_REQUIRE(op.C == ATT_C, "attn_block: only C == %d is supported in this round (got %d)", ATT_C, op.C);
   RD_REQUIRE(op.T >= 1 && op.T <= 128, "attn_block: T must be in [1,128] (got %d)", op.T);
   RD_REQUIRE(op.groups > 0 && op.C % op.groups == 0, "attn_block: bad GroupNorm geometry");
+  {
+    // tcgen05 kernel first (attn_tc.cu); RD_ATTN_TC=0 keeps the mma.sync kernel below (A/B measurements)
+    static const bool use_tc = !(getenv("RD_ATTN_TC") && atoi(getenv("RD_ATTN_TC")) == 0);
+    if (use_tc) {
+      const int rc = attn_block_tc_launch(op, st);
+      if (rc != RD_E_UNSUPPORTED) return rc;
+    }
+  }
   const float scale = 1.0f / sqrtf(static_cast<float>(op.C));
   const int t16 = (op.T + 15) / 16;
   const int tp = 16 * t16;
