@@ -53,6 +53,9 @@ constexpr int EPI_WARPS = 4;        // warps 4..7
 constexpr int MAX_A_STAGES = 3;
 constexpr int MAX_W_STAGES = 12;
 constexpr int MAX_HW = 32;                              // gather maps
+#ifndef RD_STREAM_SB
+#define RD_STREAM_SB 6  // 16-byte loads in flight per thread in the streaming statistics pass (bf16 plan)
+#endif
 constexpr int STAT_PAIRS = 256;                         // (sample, 8-channel chunk) pairs per statistics batch (streaming mode)
 constexpr int STAT_SCRATCH_BYTES = XFORM_THREADS * 64;  // one 16-float partial record per transform thread
 
@@ -76,6 +79,10 @@ struct ConvParams {
   int Wp, rps;       // padded row width, rows per sample in the staged image
   int pad;           // pixel (y,x) is staged at (y+pad, x+pad)
   int stride;        // output (oy,ox) = accumulator row (oy*stride, ox*stride)
+  // stride 2, polyphase layout: the image is staged as four parity planes (y&1, x&1) of (Ho+1) x (Wo+1) positions, `plane_rows`
+  // rows apart, so tap (dy,dx) reads plane (dy&1, dx&1) shifted by (dy>>1, dx>>1) and the accumulator rows are the OUTPUT
+  // positions only (the one-plane layout computes every input position and keeps a quarter of them)
+  int poly, plane_rows;
   int Ho, Wo;
   int ntaps;         // 9 or 1
   int Cin, KC;       // total input channels, Cin/8
@@ -361,7 +368,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
   for (int sp = tid; sp < p.S * P; sp += CONV_THREADS) {
     const int s = sp / P, px = sp - s * P;
     const int y = px / p.W, x = px - y * p.W;
-    t_row[sp] = static_cast<unsigned short>(s * p.rps + (y + p.pad) * p.Wp + (x + p.pad));
+    t_row[sp] = p.poly ? static_cast<unsigned short>(((y & 1) * 2 + (x & 1)) * p.plane_rows + s * p.rps + (y >> 1) * p.Wp + (x >> 1))
+                       : static_cast<unsigned short>(s * p.rps + (y + p.pad) * p.Wp + (x + p.pad));
     t_off[sp] = ((s * p.Hs[0] + p.ymap[0][y]) * p.Ws[0] + p.xmap[0][x]) * p.C[0];
     if (p.nsrc > 1) t_off[p.S * P + sp] = ((s * p.Hs[1] + p.ymap[1][y]) * p.Ws[1] + p.xmap[1][x]) * p.C[1];
     if (p.sc_chunks > 0) {
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
     const int Y = rem / p.Wp, X = rem - Y * p.Wp;
     bool valid = s < p.S;
     int oy = Y, ox = X;
-    if (p.stride == 2) {
+    if (p.stride == 2 && !p.poly) {
       valid = valid && ((Y & 1) == 0) && ((X & 1) == 0);
       oy = Y >> 1; ox = X >> 1;
     }
@@ -432,7 +440,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       auto keep = [](uint32_t v) { uint32_t r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v)); return r; };
       const uint32_t wfull0 = keep(smem_u32(&bar_w_full[0])), wempty0 = keep(smem_u32(&bar_w_empty[0]));
       const uint32_t afull0 = keep(smem_u32(&bar_a_full[0])), aempty0 = keep(smem_u32(&bar_a_empty[0]));
-      const uint32_t uN = static_cast<uint32_t>(N), uWp = static_cast<uint32_t>(Wp);
+      const uint32_t uN = static_cast<uint32_t>(N);
+      // tap (dy,dx) -> row shift rs[dy] + cs[dx]: dy*Wp + dx, or (polyphase stride 2) plane (dy&1, dx&1) + (dy>>1)*Wp + (dx>>1)
+      const uint32_t rs1 = p.poly ? 2u * p.plane_rows : static_cast<uint32_t>(Wp), rs2 = p.poly ? static_cast<uint32_t>(Wp) : 2u * Wp;
+      const uint32_t cs1 = p.poly ? static_cast<uint32_t>(p.plane_rows) : 1u, cs2 = p.poly ? 1u : 2u;
+      auto tap_shift = [&](int t) -> uint32_t {
+        const int dy = t / 3, dx = t % 3;  // compile-time at every call site (the tap loops are fully unrolled)
+        return (dy == 0 ? 0u : (dy == 1 ? rs1 : rs2)) + (dx == 0 ? 0u : (dx == 1 ? cs1 : cs2));
+      };
       for (int li = 0; li < my_groups; ++li) {
         const int buf = li % acc_bufs, useb = li / acc_bufs;
         if (useb > 0) { mbar_wait(&bar_acc_empty[buf], (useb - 1) & 1); tc_fence_after_sync(); }
@@ -446,7 +461,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             const uint32_t w_chunk = w_lo0 + chunk * NTAPS * w_slab_u;
 #pragma unroll
             for (int t = 0; t < NTAPS; ++t) {
-              const uint32_t shift = NTAPS == 9 ? (t / 3) * uWp + (t % 3) : 0u;  // tap (dy,dx) -> row shift dy*Wp + dx
+              const uint32_t shift = NTAPS == 9 ? tap_shift(t) : 0u;
               if (leader)
                 issue_tap<NT, TILE_OUTER, X3>(acc, uN, a_lo_stage + shift, w_chunk + t * w_slab_u, kstep_a, kstep_w, desc_hi,
                                               idesc, (chunk | t) != 0, a_half, w_half);
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
           } else {
 #pragma unroll
             for (int t = 0; t < NTAPS; ++t) {
-              const uint32_t shift = NTAPS == 9 ? (t / 3) * uWp + (t % 3) : 0u;
+              const uint32_t shift = NTAPS == 9 ? tap_shift(t) : 0u;
               mbar_wait_addr(wfull0 + 8 * ws, w_par);
               tc_fence_after_sync();
               if (leader) {
@@ -888,6 +903,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
       // ---------------- streaming mode: statistics pass, then a normalise pass per chunk (also the only transform of
       // the fp32-class mode, where a pixel's 8 channels are 32 bytes of fp32 and leave as a bf16 hi and a bf16 lo vector)
       const int a_half16 = p.a_stage_bytes / 32;  // uint4 index of the lo image inside a stage (x3)
+#ifdef RD_STREAM_NOTABLE  // measurement build: per-item coefficient look-ups as before
+      const bool coef_table = false;
+#else
+      const bool coef_table = GNM != GNM_NONE && 2 * p.S * p.Cin * 4 <= STAT_SCRATCH_BYTES;
+#endif
+      const float inv_P = 1.0f / static_cast<float>(P);
       auto load8 = [&](const act_t* ptr, uint4& raw, float (&f)[8]) {
         if constexpr (X3) ldg8f(reinterpret_cast<const float*>(ptr), f);
         else raw = __ldg(reinterpret_cast<const uint4*>(ptr));
@@ -918,7 +939,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               float sum[8], sq[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) { sum[j] = 0.0f; sq[j] = 0.0f; }
-              constexpr int SB = X3 ? 2 : 4;  // (12 in flight was measured slower: the streaming variants spill at the 128-register cap)
+              constexpr int SB = X3 ? 2 : RD_STREAM_SB;  // (12 in flight was measured slower: the streaming variants spill at the 128-register cap)
               for (int px = slice; px < P; px += SB * PS) {
                 uint4 raw[SB];
                 float f[X3 ? SB : 1][8];
@@ -945,7 +966,38 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
             stat_reduce(sb, ns, pairs, PS);
             xform_bar();
           }
+          // per-(sample, channel) affine table over the (now idle) statistics scratch: the normalise pass then costs four
+          // 16-byte shared loads per item instead of 20 scalar ones and 32 multiplies (same expressions, same values)
+          if (coef_table) {
+            for (int idx = xt; idx < S_act * p.Cin; idx += XFORM_THREADS) {
+              const int s = idx / p.Cin, c = idx - s * p.Cin;
+              const float2 mr = *reinterpret_cast<const float2*>(s_stat + 2 * (s * p.groups + s_gidx[c]));
+              float ca = s_gamma[c] * mr.y, cb = fmaf(-mr.x, ca, s_beta[c]);
+              if (p.silu) { ca *= 0.5f; cb *= 0.5f; }
+              s_scr[idx] = ca;
+              s_scr[p.S * p.Cin + idx] = cb;
+            }
+            xform_bar();
+          }
         }
+        // warm the L2 with the next group's pixels: its statistics pass otherwise waits for HBM, batch after batch
+#ifndef RD_STREAM_NOPF  // (measurement build without the prefetch)
+        if (li + 1 < my_groups) {
+          const int gn = g + gridDim.x;
+          const int S_n = max(0, min(p.S, p.B2 - gn * p.S));
+          constexpr int EPL = 128 / static_cast<int>(sizeof(act_t));  // elements per 128-byte line
+          for (int which = 0; which < p.nsrc; ++which) {
+            const act_t* base = (which ? src1 + static_cast<size_t>(gn) * gstride1 : src0 + static_cast<size_t>(gn) * gstride0);
+            const int lpp = p.C[which] / EPL;  // lines per pixel
+            if (lpp * EPL != p.C[which]) continue;
+            const int* toff = t_off + (which ? p.S * P : 0);
+            for (int i = xt; i < S_n * P * lpp; i += XFORM_THREADS) {
+              const int sp = i / lpp, l = i - sp * lpp;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(base + toff[sp] + l * EPL));
+            }
+          }
+        }
+#endif
         const int items = S_act * P * 8;
         for (int chunk = 0; chunk < p.nchunks; ++chunk, ++a_it) {
           const int stage = a_it % p.a_stages;
@@ -969,7 +1021,19 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const __grid
               if (item < items) {
                 const int sp = item >> 3, kcl = item & 7;
                 float ca[8], cb[8];
-                if (GNM != GNM_NONE) gn_coeffs(sp / P, chunk * 64 + kcl * 8, ca, cb);
+                if (GNM != GNM_NONE) {
+                  const int smp = __float2int_rz((static_cast<float>(sp) + 0.5f) * inv_P);  // sp / P, exact for these sizes
+                  if (coef_table) {
+                    const float* ta = s_scr + smp * p.Cin + chunk * 64 + kcl * 8;
+                    const float* tb = ta + p.S * p.Cin;
+                    const float4 a0 = *reinterpret_cast<const float4*>(ta), a1 = *reinterpret_cast<const float4*>(ta + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(tb), b1 = *reinterpret_cast<const float4*>(tb + 4);
+                    ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+                    cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
+                  } else {
+                    gn_coeffs(smp, chunk * 64 + kcl * 8, ca, cb);
+                  }
+                }
                 if constexpr (X3) {
                   if (GNM != GNM_NONE) gn_apply_f(f[u], ca, cb);
                   uint4 hi, lo;
@@ -1112,7 +1176,6 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
   // accumulators can be double-buffered (2*nt*N <= 512 columns) and whether the whole filter stays
   // resident in shared memory.  Score = useful rows per MMA row, discounted when the epilogue cannot
   // overlap the next group's MMAs.
-  const int max_shift = (op.ntaps == 9) ? 2 * p.Wp + 2 : 0;
   const int smem_cap = 227 * 1024 - 2048;  // static __shared__ barriers + alignment slack
   const int valid_px = op.H_out * op.W_out;
   double best_score = -1.0;
@@ -1131,12 +1194,19 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
       if (q) ++q;
     }
   }
+  // stride 2 (bf16 plan): polyphase layout first, the one-plane layout if no polyphase geometry fits (RD_CONV_POLY=0: A/B runs)
+  static const int poly_on = env_int("RD_CONV_POLY", 1);
+  for (int poly = (op.stride == 2 && !p.x3 && poly_on) ? 1 : 0; poly >= 0 && best_score < 0; --poly) {
+  if (poly) { p.poly = 1; p.Wp = op.W_out + 1; p.rps = (op.H_out + 1) * p.Wp; p.pad = 0; }
+  else if (p.poly) { p.poly = 0; p.Wp = op.W_in + 1; p.rps = (op.H_in + 1) * p.Wp; p.pad = op.pad ? 1 : 0; }
+  const int max_shift = p.poly ? p.Wp + 1 : ((op.ntaps == 9) ? 2 * p.Wp + 2 : 0);
   for (int nt = 1; nt <= 4; ++nt) {
     if (nt * p.N > 512 || nt * 128 < p.rps) continue;
     if (force_nt && nt != force_nt) continue;
     ConvParams c = p;
     c.n_tiles = nt;
-    c.R = (nt * 128 + max_shift) | 1;
+    c.plane_rows = nt * 128 + max_shift;
+    c.R = ((p.poly ? 4 : 1) * c.plane_rows) | 1;
     c.S = (nt * 128) / p.rps;
     if (op.samples_per_cta > 0 && op.samples_per_cta < c.S) c.S = op.samples_per_cta;
     // the per-group (bias + temb) table is S x N floats, double-buffered: keep it within 32 KB (only reached at 1x1 / 2x2
@@ -1159,12 +1229,15 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
       // leave, up to `wmax` slabs.
       c.w_resident = 0;
       if (c.a_stages > astream) c.a_stages = astream;
+      if (p.poly && c.a_stages > 2) c.a_stages = 2;  // a polyphase stage is four planes: two stages and a full filter ring
       c.w_stages = wmax < p.n_slabs ? wmax : p.n_slabs;
       if (c.w_stages < 2) c.w_stages = 2;
       while (c.w_stages > 2 && conv_smem_layout(c).total > smem_cap) --c.w_stages;
       if (conv_smem_layout(c).total > smem_cap && c.a_stages == 3) c.a_stages = 2;
       if (conv_smem_layout(c).total > smem_cap) c.a_stages = 1;  // last resort (fp32-class plan at 16x16): transform and MMAs alternate
       if (conv_smem_layout(c).total > smem_cap) continue;
+      // the plain gather stages chunk i+1 before it reports chunk i: it needs two stages
+      if (c.a_stages == 1 && !p.x3 && p.groups == 0) continue;
     }
     // transform mode: team mode (bf16 plan, GroupNorm groups of 4 / 8 channels) when the S x 8 (sample, item) teams of a
     // chunk fit the 320 transform threads with at most 16 pixels per lane; otherwise the two-pass streaming transform
@@ -1178,8 +1251,10 @@ int conv_make_params(const rd_op_conv& op, ConvParams& p, int& smem_bytes, int& 
     if (p.sc_chunks > 0 && c.xmode == 0) continue;  // the fused shortcut is staged by the team-mode transform only
     double score = static_cast<double>(c.S * valid_px) / (nt * 128);
     if (c.acc_bufs == 1) score *= 0.75;
+    if (c.a_stages == 1) score *= 0.6;  // staging and MMAs alternate
     if (!c.w_resident) score *= (nt >= 2 ? 0.97 : 0.85);  // streamed weights are re-read per group: favour larger groups
     if (score > best_score) { best_score = score; best = c; }
+  }
   }
   RD_REQUIRE(best_score > 0, "conv: no tile geometry fits (Cin=%d N=%d rps=%d x3=%d)", cin, p.N, p.rps, p.x3);
   p = best;

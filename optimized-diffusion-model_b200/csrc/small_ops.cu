@@ -9,6 +9,8 @@
 #include <cuda_bf16.h>
 #include "rd_ptx.cuh"
 #include <type_traits>
+#include <cstdlib>
+#include <cstdint>
 
 namespace rd {
 
@@ -406,6 +408,165 @@ __global__ void __launch_bounds__(2 * OH_WARPS * 32, 4) out_head_kernel(const TI
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// out head, bf16 plan at the GTO-Halo shape (C = 64, 16 groups of 4 channels, one image channel, <= 88 pixels): one warp
+// per guided sample, everything in registers.  The warp reads the sample's [P][64] bf16 image ONCE, laid out as the B
+// fragments of mma.sync.m16n8k16 (N = 8 pixels per block, K = 16 channels per k-block): lane (g, q) holds pixel 8 nb + g,
+// channels 16 kb + 4 q .. + 3.  A GroupNorm group (four adjacent channels) is then one register pair, its statistics a
+// per-lane sum over the pixel blocks plus three shuffles over g.  The nine per-tap dot products q[tap][px] = sum_c
+// w[tap][c] act[c][px] are ONE M = 16 (taps, 9 used) x N = 8 (pixels) x K = 64 product per pixel block with fp32-class
+// operands: act and w are split into bf16 hi + lo and accumulated as lo*hi + hi*lo + hi*hi in fp32 (2^-17 relative, the
+// scheme of temb_kernel).  This replaces the 14 shuffles + ~25 selects per pixel of the SIMT warp reduction: ~25 warp
+// instructions per pixel instead of ~100.  The conv output is the 9-term gather of q over the 3x3 neighbourhood, then the
+// reference's guidance combine.  The k index of the product is a permutation of the channels (fragment positions 2q, 2q+1,
+// 2q+8, 2q+9 <-> channels 4q .. 4q+3) so that a lane's four channels are one 8-byte load.
+template <int NB>
+__global__ void __launch_bounds__(128, 3) out_head_mma_kernel(const __nv_bfloat16* __restrict__ h, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ cfg_w,
+                                                             float cfg_w_scalar, float* __restrict__ score, int B, int H, int W,
+                                                             int cfg, float eps, const float* __restrict__ sigma_table,
+                                                             const int32_t* __restrict__ step_ctr) {
+  constexpr int C = 64, QP = 8 * NB;
+  __shared__ __align__(16) uint32_t s_wf[4][2][32][4];  // [k-block][hi|lo][lane][a0..a3]
+  __shared__ __align__(16) float s_q[4][9][QP];         // [warp][tap][pixel]
+  __shared__ __align__(16) float s_gb[2][C];            // gamma, beta
+  __shared__ __align__(16) float s_ab[4][2][C];         // [warp][a|b][channel]: y = x a + b of the current (sample, pass)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int P = H * W;
+  for (int i = tid; i < 4 * 32 * 4; i += 128) {
+    const int r = i & 3, ln = (i >> 2) & 31, kb = i >> 7;
+    const int tap = (ln >> 2) + ((r & 1) ? 8 : 0), ch = 16 * kb + 4 * (ln & 3) + ((r & 2) ? 2 : 0);
+    const float w0 = tap < 9 ? w[ch * 9 + tap] : 0.0f, w1 = tap < 9 ? w[(ch + 1) * 9 + tap] : 0.0f;
+    __nv_bfloat16 h0, l0, h1, l1;
+    te_split(w0, h0, l0);
+    te_split(w1, h1, l1);
+    s_wf[kb][0][ln][r] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+    s_wf[kb][1][ln][r] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+  }
+  if (tid < C) { s_gb[0][tid] = gamma[tid]; s_gb[1][tid] = beta[tid]; }
+  __syncthreads();
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= B) return;
+  const int npass = cfg ? 2 : 1;
+  float* qs = &s_q[warp][0][0];
+  const float inv_n = 1.0f / static_cast<float>(4 * P);
+  float r0[3] = {0.0f, 0.0f, 0.0f};
+  const float bias0 = bias[0];
+  const float sig0 = sigma_table ? (step_ctr ? sigma_table[*step_ctr] : sigma_table[b]) : 1.0f;
+  const float sig1 = sigma_table ? (step_ctr ? sig0 : sigma_table[b + B]) : 1.0f;
+
+  for (int ps = 0; ps < npass; ++ps) {
+    const __nv_bfloat16* hb = h + static_cast<size_t>(b + ps * B) * P * C + 4 * q;
+    uint2 x[NB][4];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const int px = 8 * nb + g;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb)
+        x[nb][kb] = px < P ? __ldg(reinterpret_cast<const uint2*>(hb + static_cast<size_t>(px) * C + 16 * kb)) : make_uint2(0u, 0u);
+    }
+    // ---- GroupNorm statistics: the lane's four channels 16kb + 4q .. + 3 are one group; pixels beyond P contribute zeros
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const float a0 = __uint_as_float(x[nb][kb].x << 16), a1 = __uint_as_float(x[nb][kb].x & 0xffff0000u);
+        const float b0 = __uint_as_float(x[nb][kb].y << 16), b1 = __uint_as_float(x[nb][kb].y & 0xffff0000u);
+        s1 += (a0 + a1) + (b0 + b1);
+        s2 = fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, fmaf(b1, b1, s2))));
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const float mean = s1 * inv_n;
+      const float rstd = 1.0f / sqrtf(fmaxf(s2 * inv_n - mean * mean, 0.0f) + eps);
+      const float4 ga = *reinterpret_cast<const float4*>(&s_gb[0][16 * kb + 4 * q]);
+      const float4 be = *reinterpret_cast<const float4*>(&s_gb[1][16 * kb + 4 * q]);
+      if (g == 0) {  // (the eight lanes that share q hold the same values)
+        const float4 a4 = make_float4(ga.x * rstd, ga.y * rstd, ga.z * rstd, ga.w * rstd);
+        *reinterpret_cast<float4*>(&s_ab[warp][0][16 * kb + 4 * q]) = a4;
+        *reinterpret_cast<float4*>(&s_ab[warp][1][16 * kb + 4 * q]) =
+            make_float4(fmaf(-mean, a4.x, be.x), fmaf(-mean, a4.y, be.y), fmaf(-mean, a4.z, be.z), fmaf(-mean, a4.w, be.w));
+      }
+    }
+    __syncwarp();
+    // ---- per pixel block: normalise + SiLU + split, q[tap][px] on the tensor core
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        float v[4] = {__uint_as_float(x[nb][kb].x << 16), __uint_as_float(x[nb][kb].x & 0xffff0000u),
+                      __uint_as_float(x[nb][kb].y << 16), __uint_as_float(x[nb][kb].y & 0xffff0000u)};
+        const float4 ca4 = *reinterpret_cast<const float4*>(&s_ab[warp][0][16 * kb + 4 * q]);
+        const float4 cb4 = *reinterpret_cast<const float4*>(&s_ab[warp][1][16 * kb + 4 * q]);
+        const float ca[4] = {ca4.x, ca4.y, ca4.z, ca4.w}, cb[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
+        uint32_t bh[2], bl[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float a[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float y = fmaf(v[2 * j + e], ca[2 * j + e], cb[2 * j + e]);
+            a[e] = __fdividef(y, 1.0f + __expf(-y));
+          }
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(a[0], a[1]);
+          const float2 hf = __bfloat1622float2(hi);
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(a[0] - hf.x, a[1] - hf.y);
+          bh[j] = *reinterpret_cast<const uint32_t*>(&hi);
+          bl[j] = *reinterpret_cast<const uint32_t*>(&lo);
+        }
+        const uint4 wh = *reinterpret_cast<const uint4*>(&s_wf[kb][0][lane][0]);
+        const uint4 wl = *reinterpret_cast<const uint4*>(&s_wf[kb][1][lane][0]);
+        const uint32_t ah[4] = {wh.x, wh.y, wh.z, wh.w}, al[4] = {wl.x, wl.y, wl.z, wl.w};
+        te_mma(d, al, bh[0], bh[1]);  // small terms first
+        te_mma(d, ah, bl[0], bl[1]);
+        te_mma(d, ah, bh[0], bh[1]);
+      }
+      *reinterpret_cast<float2*>(qs + g * QP + 8 * nb + 2 * q) = make_float2(d[0], d[1]);
+      if (g == 0) *reinterpret_cast<float2*>(qs + 8 * QP + 8 * nb + 2 * q) = make_float2(d[2], d[3]);
+    }
+    __syncwarp();
+    // ---- 9-term gather per output pixel (+ scale_by_sigma), guidance combine after the second pass
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int px = lane + 32 * k;
+      if (px < P) {
+        const int y = px / W, xx0 = px - y * W;
+        float acc = bias0;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const int yy = y + dy - 1;
+          if (yy < 0 || yy >= H) continue;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int xx = xx0 + dx - 1;
+            if (xx < 0 || xx >= W) continue;
+            acc += qs[(dy * 3 + dx) * QP + yy * W + xx];
+          }
+        }
+        const float r = sigma_table ? __fdiv_rn(acc, ps ? sig1 : sig0) : acc;
+        if (ps == 0 && npass == 2) {
+          r0[k] = r;
+        } else {
+          float v = r;
+          if (npass == 2) {
+            const float wv = cfg_w ? cfg_w[b] : cfg_w_scalar;
+            v = __fsub_rn(__fmul_rn(__fadd_rn(1.0f, wv), r0[k]), __fmul_rn(wv, r));
+          }
+          score[static_cast<size_t>(b) * P + px] = v;
+        }
+      }
+    }
+    __syncwarp();  // the next pass overwrites q
+  }
+}
+
 int outhead_launch(const rd_op_outhead& op, cudaStream_t st) {
   RD_REQUIRE(op.h && op.gamma && op.beta && op.w && op.bias && op.score, "out_head: null pointer");
   RD_REQUIRE(op.groups > 0 && op.C % op.groups == 0 && op.C % 64 == 0, "out_head: C must be a multiple of 64 and of the group count");
@@ -415,6 +576,20 @@ int outhead_launch(const rd_op_outhead& op, cudaStream_t st) {
   const int smem = (2 * op.C_img * P * 9 + 2 * OH_WARPS * op.C * 2 + 2 * op.groups * 2) * 4;
   RD_REQUIRE(smem <= 48 * 1024, "out_head: image too large for shared memory");
   const int threads = (op.cfg ? 2 : 1) * OH_WARPS * 32;
+  // bf16 plan at the GTO-Halo shape: one warp per sample on mma.sync (RD_OUTHEAD_MMA=0 keeps the general kernel: A/B runs)
+  static const bool use_mma = !(getenv("RD_OUTHEAD_MMA") && atoi(getenv("RD_OUTHEAD_MMA")) == 0);
+  if (use_mma && op.precision != RD_PREC_F32X3 && op.C == 64 && op.groups == 16 && op.C_img == 1 && P <= 88 &&
+      (reinterpret_cast<uintptr_t>(op.h) & 7) == 0) {
+    const __nv_bfloat16* hp = static_cast<const __nv_bfloat16*>(op.h);
+    const int grid = (op.B + 3) / 4;
+    if (P <= 72)
+      out_head_mma_kernel<9><<<grid, 128, 0, st>>>(hp, op.gamma, op.beta, op.w, op.bias, op.cfg_w, op.cfg_w_scalar, op.score, op.B, op.H,
+                                                   op.W, op.cfg, op.eps, op.sigma_table, op.step_ctr);
+    else
+      out_head_mma_kernel<11><<<grid, 128, 0, st>>>(hp, op.gamma, op.beta, op.w, op.bias, op.cfg_w, op.cfg_w_scalar, op.score, op.B, op.H,
+                                                    op.W, op.cfg, op.eps, op.sigma_table, op.step_ctr);
+    return check_launch("out_head_mma_kernel");
+  }
   if (op.precision == RD_PREC_F32X3)
     out_head_kernel<float><<<op.B, threads, smem, st>>>(static_cast<const float*>(op.h), op.gamma, op.beta, op.w, op.bias, op.cfg_w,
                                                         op.cfg_w_scalar, op.score, op.B, op.C, op.C_img, op.H, op.W, op.groups, op.cfg,
