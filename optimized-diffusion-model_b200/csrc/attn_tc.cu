@@ -10,7 +10,7 @@
 //   u^T     = [Wpv ; 0] Xn^T       N = TP,  K = 64     columns 0..TP-1, lanes 0..63      Wpv = Wp Wv (64 x 64)
 //   [q | k] = Xn  [Wq ; Wk]^T      N = 128, K = 64     columns 0..127
 //   S       = Q K^T                N = TP,  K = 64     columns 0..TP-1
-//   Y       = Pn U                 N = 64,  K = TP     columns 0..63                      Pn = softmax rows (normalised)
+//   Y       = P U                  N = 64,  K = TP     columns 0..63                      P = exp(scale (s - max)), rows normalised in the epilogue
 //
 // (TP = T rounded up to 16.)  The output projection is folded into the value projection -- softmax(.) (Xn Wv^T) Wp^T =
 // softmax(.) (Xn (Wp Wv)^T) -- which removes one product, one accumulator read and one operand write per sample; the
@@ -23,8 +23,8 @@
 // is zero for keys >= T; score columns >= T are masked by the softmax.  Shared memory per pipeline: the A-side image (Xn,
 // then Q, then Pn), the u^T image, and the k image, which doubles as the landing buffer of the next sample's rows (one
 // bulk copy, issued as soon as S = Q K^T has consumed the keys).  The residual is re-read from global memory (L2) by the
-// thread that owns the row.  Rounding points: q, k, u, Pn in bf16 (the mma.sync kernel in attn_core.cu, kept for A/B runs
-// and for shapes this kernel does not cover, rounds v, un-normalised P and the normalised attention output instead).
+// thread that owns the row.  Rounding points: q, k, u, P (un-normalised, <= 1) in bf16 (the mma.sync kernel in attn_core.cu, kept for A/B runs
+// and for shapes this kernel does not cover, rounds v, P and the normalised attention output instead).
 #include "rd_common.h"
 #include "rd_ptx.cuh"
 #include <cuda_bf16.h>
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
   }
   // rows >= T of the A-side image stay zero for the kernel's lifetime (nothing below writes them)
   for (int i = r; i < static_cast<int>(L::k_off) / 16; i += 128) *reinterpret_cast<uint4*>(P0 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
-  if (tid < C) { s_bq[tid] = bqkv[tid]; s_bp[tid] = bproj[tid]; s_ga[tid] = gamma[tid]; s_be[tid] = beta[tid]; }
+  if (tid < C) { s_bq[tid] = bqkv[tid]; s_bp[tid] = bproj[tid] * out_scale; s_ga[tid] = gamma[tid]; s_be[tid] = beta[tid]; }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();  // the only CTA-wide barrier: from here on the pipelines run independently
@@ -385,7 +385,8 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
       tc_mma<4>(tmem, As, LBO_A, Ks, L::LBO_K, idesc_tp);  // S = Q K^T
       umma_commit(bar);
     }
-    // the residual: this thread's raw row, again (L2), in flight while the products run
+    // the residual: this thread's raw row, again (the bulk copy left it in L2), in flight while the products run.  (Requested
+    // after the softmax instead -- 32 fewer live registers there -- it was measured 3 % slower: 0.285 vs 0.276 ms per block.)
     u32x8 xres[4];
     if (row_ok) {
       const __nv_bfloat16* xrow = x + (static_cast<size_t>(b) * T + r) * C;
@@ -398,7 +399,8 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
     if (r == 0 && b + bstep < B2) prefetch(b + bstep);
 
     // ---- softmax_j(scale * s_ij) over the T valid keys of this thread's row: maximum on the raw scores (scale > 0),
-    // exp(scale (s - m)) as one FMA + ex2, normalised before rounding
+    // exp(scale (s - m)) as one FMA + ex2; the row sum (of the unrounded values) divides Y in the epilogue
+    float y_scale = 0.0f;
     if (warp_ok) {
       uint32_t v[TP];
       tmem_ld_cols<TP>(tm_lane, v);
@@ -413,13 +415,13 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
         l4[i & 3] += p;
         v[i] = __float_as_uint(p);
       }
-      const float il = 1.0f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
+      y_scale = out_scale / ((l4[0] + l4[1]) + (l4[2] + l4[3]));  // 1 / row sum: applied to Y in the epilogue
       if (row_ok) {
 #pragma unroll
         for (int sg = 0; sg < NSEG; ++sg) {
           uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = tc_pack(__uint_as_float(v[8 * sg + 2 * e]) * il, __uint_as_float(v[8 * sg + 2 * e + 1]) * il);
+          for (int e = 0; e < 4; ++e) o[e] = tc_pack(__uint_as_float(v[8 * sg + 2 * e]), __uint_as_float(v[8 * sg + 2 * e + 1]));
           st_shared_v4(As + r * 16 + sg * LBO_A, o[0], o[1], o[2], o[3]);
         }
       }
@@ -428,13 +430,13 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
     TCA_MARK(8);
     if (r == 0) {
       tc_fence_after_sync();
-      tc_mma<T16>(tmem, As, LBO_A, Vs, LBO_V, idesc_c);  // Y = Pn U
+      tc_mma<T16>(tmem, As, LBO_A, Vs, LBO_V, idesc_c);  // Y = P U
       umma_commit(bar);
     }
     product_done();
     TCA_MARK(9);
 
-    // ---- (x + y + bias) * out_scale -> this thread's output row (4 x 32 bytes)
+    // ---- (x + y / l + bias) * out_scale -> this thread's output row (4 x 32 bytes)
     if (warp_ok) {
       uint32_t v[64];
       tmem_ld_cols<64>(tm_lane, v);
@@ -447,8 +449,8 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
           for (int e = 0; e < 8; ++e) {
             const int c = 16 * j + 2 * e;
             const uint32_t xr = xres[j].v[e];
-            o.v[e] = tc_pack((__uint_as_float(xr << 16) + __uint_as_float(v[c]) + s_bp[c]) * out_scale,
-                             (__uint_as_float(xr & 0xffff0000u) + __uint_as_float(v[c + 1]) + s_bp[c + 1]) * out_scale);
+            o.v[e] = tc_pack(fmaf(__uint_as_float(xr << 16), out_scale, fmaf(__uint_as_float(v[c]), y_scale, s_bp[c])),
+                             fmaf(__uint_as_float(xr & 0xffff0000u), out_scale, fmaf(__uint_as_float(v[c + 1]), y_scale, s_bp[c + 1])));
           }
           st_global_256(orow + 16 * j, o);
         }

@@ -52,24 +52,41 @@ __global__ void __launch_bounds__(256, 2) temb_kernel(const float* __restrict__ 
   const int wm = warp & 3, wn = warp >> 2;  // warp tile: rows wm*32..+31, columns wn*64..+63
   float acc[2][8][4] = {};
   // every thread stages 8 A and 8 B elements per k-tile (element = (row, k)); the next tile's global reads are
-  // issued before the current tile's MMAs
+  // issued before the current tile's MMAs.  A thread's eight elements share one k (= k0 + tid % 16) and sit in eight
+  // fixed rows, so everything per-row (time-table row, label) is looked up once and everything per-k once per tile.
   float pa[8], pb[8];
+  const int kk = tid & (TE_BK - 1);
+  int a_row[8];    // time-table row offset (elements) or -1: row outside the batch
+  float a_lab[8];  // the sample's label (one class) -- more classes take the general loop below
+  int b_off[8];    // filter row offset (elements) or -1
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int mm = (tid + u * 256) >> 4;
+    const int b = m0 + mm, o = n0 + mm;
+    a_row[u] = b < B2 ? (row_idx ? row_idx[b] : step) * K : -1;
+    a_lab[u] = (b < B2 && NC == 1) ? labels[b] : 0.0f;
+    b_off[u] = o < NO ? o * K : -1;
+  }
+  auto fast_silu = [](float v) { return __fdividef(v, 1.0f + __expf(-v)); };  // ~3e-7 relative: below the 2^-17 operand split
   auto fetch = [&](int k0) {
+    const int k = k0 + kk;
+    const bool k_ok = k < K;
+    const float lw = (k_ok && NC == 1) ? label_w[k] : 0.0f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int i = tid + u * 256;
-      const int kk = i & (TE_BK - 1), mm = i >> 4;
-      const int b = m0 + mm, k = k0 + kk;
       float t = 0.0f;
-      if (b < B2 && k < K) {
-        const int row = row_idx ? row_idx[b] : step;
-        t = time_table[static_cast<size_t>(row) * K + k];
-        for (int c = 0; c < NC; ++c) t = fmaf(label_w[k * NC + c], labels[static_cast<size_t>(b) * NC + c], t);
-        t = silu_acc(t);
+      if (a_row[u] >= 0 && k_ok) {
+        t = time_table[a_row[u] + k];
+        if (NC == 1) {
+          t = fmaf(lw, a_lab[u], t);
+        } else {
+          const int b = m0 + ((tid + u * 256) >> 4);
+          for (int c = 0; c < NC; ++c) t = fmaf(label_w[k * NC + c], labels[static_cast<size_t>(b) * NC + c], t);
+        }
+        t = fast_silu(t);
       }
       pa[u] = t;
-      const int o = n0 + mm;
-      pb[u] = (o < NO && k < K) ? dense_w[static_cast<size_t>(o) * K + k] : 0.0f;
+      pb[u] = (b_off[u] >= 0 && k_ok) ? dense_w[b_off[u] + k] : 0.0f;
     }
   };
   fetch(0);

@@ -420,3 +420,52 @@ def test_two_devices_in_one_process():
         xs, _ = fn(model, weight=1.5, class_labels=labels.to(d), rd_seed=4)
         assert xs.device == torch.device(d) and bool(cube.inside(xs).all())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+# ------------------------------------------------------------------------------------------------ output head on mma.sync
+_HEAD_SCRIPT = r"""
+import sys, types, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2]); sys.path.insert(0, sys.argv[3])
+import sde_lib
+from models import utils as mutils
+from oracle import rd_oracle as O
+from helpers import make_config, oracle_cfg
+isz, scale_by_sigma = int(sys.argv[4]), bool(int(sys.argv[5]))
+torch.manual_seed(0)
+cfg = make_config(isz, isz, "langevin", scale_by_sigma=scale_by_sigma)
+sd = O.synth_state_dict(oracle_cfg(isz, isz, scale_by_sigma=scale_by_sigma), seed=7, out_scale=1.0)
+model = mutils.create_model(cfg).to("cuda"); model.load_state_dict(sd); model.eval()
+sde = sde_lib.RVESDE(sigma_min=0.01, sigma_max=5.0, N=1000)
+B = 37   # not a multiple of the four samples per CTA
+x = torch.rand(B, 1, isz, 9, device="cuda"); labels = torch.rand(B, 1, device="cuda")
+t = torch.linspace(0.05, 1.0, B, device="cuda")
+w = torch.linspace(0.0, 4.0, B, device="cuda")
+with torch.no_grad():
+    s = mutils.get_cf_score_fn(sde, model, labels, w)(x, t)
+torch.save(s.cpu(), sys.argv[6])
+"""
+
+
+@pytest.mark.parametrize("isz,scale_by_sigma", [(8, False), (9, False), (8, True)])
+def test_out_head_mma_matches_general_kernel(tmp_path, isz, scale_by_sigma):
+    """The one-warp-per-sample output head (mma.sync, split-bf16 operands, csrc/small_ops.cu out_head_mma_kernel) against the
+    general fp32 SIMT kernel on the same network activations (RD_OUTHEAD_MMA=0, read once per process -> two subprocesses):
+    out_norm + SiLU + out_conv + guidance combine (ncsnpp.py:343-351, models/utils.py:124-138).  Both heads read the same
+    bf16 activations, so they may differ only by the 2^-17 operand split and the summation order (a few 1e-6 per network
+    pass), which the guidance combine (1 + w) a - w b amplifies by up to 1 + 2w = 9 here: bound 5e-5 of the largest score
+    (measured 2.2e-5)."""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    outs = []
+    for flag in ("1", "0"):
+        out = str(tmp_path / f"score_{flag}.pt")
+        env = dict(os.environ, RD_OUTHEAD_MMA=flag)
+        r = subprocess.run([sys.executable, "-c", _HEAD_SCRIPT, root, os.path.join(root, "optimized-diffusion-model_b200"), here,
+                            str(isz), str(int(scale_by_sigma)), out], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(out))
+    a, b = outs
+    assert torch.isfinite(a).all() and a.abs().max() > 0
+    err = float((a - b).abs().max() / b.abs().max())
+    assert err <= 5e-5, f"mma output head deviates from the general kernel: {err:.3e} of max"
