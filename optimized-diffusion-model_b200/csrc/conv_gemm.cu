@@ -26,6 +26,14 @@
 //     samples, so the A operand of tap (dy,dx) is the same buffer with the UMMA descriptor start
 //     address advanced by (dy*Wp+dx)*16 B: nine taps, no im2col, no data movement (validated on B200 by
 //     tools/probe_umma.cu).  Outputs at padding rows are computed and dropped.
+//   * Stride 2 (Downsample): the image is staged as its four parity planes (y&1, x&1) of (Ho+1) x (Wo+1) positions, one
+//     after the other in the same buffer, so tap (dy,dx) is plane (dy&1, dx&1) advanced by ((dy>>1)*Wp + (dx>>1)) rows
+//     and the accumulator rows are the OUTPUT positions only (a one-plane layout computes all H x W positions and keeps
+//     a quarter: 0.155 -> 0.090 ms for the 8x9 -> 4x4 launch).  Still nine descriptor offsets, still no data movement.
+//   * GroupNorm groups that do not align with the 8-channel operand items (192 channels / 32 groups = 6) and the fp32-class
+//     plan take the streaming transform: a statistics pass (fixed-order shared-memory reduction), a per-(sample, channel)
+//     affine table written over the idle statistics scratch, then a normalise pass per 64-channel chunk that reads its
+//     coefficients with four 16-byte shared loads per item; the next group's pixels are requested into L2 meanwhile.
 //   * All index arithmetic is group-invariant and tabulated once per CTA in shared memory.
 //   * Two precisions (template parameter X3).  bf16: bf16 NHWC activations, one MMA per k-step.  fp32-class ("x3"):
 //     fp32 NHWC activations; both operands are split into bf16 hi + bf16 lo (x = hi + lo to 2^-17) and every k-step
