@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
   const int warp = r >> 5;        // warp within the warpgroup = TMEM lane quarter
   unsigned char* P0 = sm + L::pipes_off + pipe * L::pipe_bytes;
   unsigned char* Stg = P0 + L::k_off;  // the next sample's rows land in the k image once S = Q K^T is done
-  float* s_pt = reinterpret_cast<float*>(P0 + L::f_off);  // [4][2][C] per-warp channel sums
+  float* s_ab = reinterpret_cast<float*>(P0 + L::f_off);  // [2][C]: GroupNorm affine (a, b) of the pipeline's current / next sample
   float* s_bq = reinterpret_cast<float*>(sm + L::par_off);
   float* s_bp = s_bq + C;
   float* s_ga = s_bp + C;
@@ -215,88 +215,62 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
     tc_fence_before_sync();
     pipe_sync();
   };
-#ifdef RD_TCA_PROF
-  long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = clock64();
-  int nsamp = 0;
-#endif
-
-  for (int b = b0; b < B2; b += bstep) {
-    mbar_wait(bar_x, xpar);  // this sample's rows have landed
+  // GroupNorm statistics of the sample whose rows are landing, by warp 3 alone: with T <= 96 tokens this warp owns no query
+  // row, so the statistics run on the otherwise idle fourth scheduler, beside the softmax / last product / epilogue of the
+  // sample before -- off the pipeline's critical path.  Lane = (8-channel segment, row slot 0..3); result: the table
+  // s_ab[0..63] = a, s_ab[64..127] = b with y = x a + b.
+  auto sample_stats = [&]() {
+    mbar_wait(bar_x, xpar);
     xpar ^= 1;
-    TCA_MARK(0);
-
-    // ---- GroupNorm: per-warp channel sums -> shared memory -> every thread forms the affine of its own 8 channels
-    uint4 raw[T16];
-    {
-      float s1[8], s2[8];
+    const int sseg = lane & 7, rs4 = lane >> 3;
+    float c1[8], c2[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] = 0.0f; s2[j] = 0.0f; }
+    for (int j = 0; j < 8; ++j) { c1[j] = 0.0f; c2[j] = 0.0f; }
+#pragma unroll 4
+    for (int row = rs4; row < T; row += 4) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(Stg + row * 128 + sseg * 16);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-      for (int k = 0; k < T16; ++k) {
-        const int row = rsub + 16 * k;
-        raw[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (row < T) raw[k] = *reinterpret_cast<const uint4*>(Stg + row * 128 + seg * 16);
-        const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
-          s1[2 * j] += lo; s2[2 * j] = fmaf(lo, lo, s2[2 * j]);
-          s1[2 * j + 1] += hi; s2[2 * j + 1] = fmaf(hi, hi, s2[2 * j + 1]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8); s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
-        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
-      }
-      if (lane < 8) {
-        float4* d1 = reinterpret_cast<float4*>(s_pt + warp * 2 * C + seg * 8);
-        float4* d2 = reinterpret_cast<float4*>(s_pt + warp * 2 * C + C + seg * 8);
-        d1[0] = make_float4(s1[0], s1[1], s1[2], s1[3]); d1[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
-        d2[0] = make_float4(s2[0], s2[1], s2[2], s2[3]); d2[1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+        c1[2 * j] += lo; c2[2 * j] = fmaf(lo, lo, c2[2 * j]);
+        c1[2 * j + 1] += hi; c2[2 * j + 1] = fmaf(hi, hi, c2[2 * j + 1]);
       }
     }
-    pipe_sync();
-    TCA_MARK(1);
-    {
-      float c1[8], c2[8];  // sums over the sample of this thread's 8 channels, then of their groups
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { c1[j] = 0.0f; c2[j] = 0.0f; }
+    for (int j = 0; j < 8; ++j) {
+      c1[j] += __shfl_xor_sync(0xffffffffu, c1[j], 8); c1[j] += __shfl_xor_sync(0xffffffffu, c1[j], 16);
+      c2[j] += __shfl_xor_sync(0xffffffffu, c2[j], 8); c2[j] += __shfl_xor_sync(0xffffffffu, c2[j], 16);
+    }
+    // group sums: butterflies inside the lane's 8 channels, then across the lanes that hold the group's other segments
+    if (cpg >= 2) {
+      float t1[8], t2[8];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const float4 p0 = *reinterpret_cast<const float4*>(s_pt + w * 2 * C + seg * 8), p1 = *reinterpret_cast<const float4*>(s_pt + w * 2 * C + seg * 8 + 4);
-        const float4 q0 = *reinterpret_cast<const float4*>(s_pt + w * 2 * C + C + seg * 8), q1 = *reinterpret_cast<const float4*>(s_pt + w * 2 * C + C + seg * 8 + 4);
-        c1[0] += p0.x; c1[1] += p0.y; c1[2] += p0.z; c1[3] += p0.w; c1[4] += p1.x; c1[5] += p1.y; c1[6] += p1.z; c1[7] += p1.w;
-        c2[0] += q0.x; c2[1] += q0.y; c2[2] += q0.z; c2[3] += q0.w; c2[4] += q1.x; c2[5] += q1.y; c2[6] += q1.z; c2[7] += q1.w;
-      }
-      // group sums: butterflies inside the thread's 8 channels, then across the lanes that hold the group's other segments
-      if (cpg >= 2) {
-        float t1[8], t2[8];
+      for (int j = 0; j < 8; ++j) { t1[j] = c1[j] + c1[j ^ 1]; t2[j] = c2[j] + c2[j ^ 1]; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { t1[j] = c1[j] + c1[j ^ 1]; t2[j] = c2[j] + c2[j ^ 1]; }
+      for (int j = 0; j < 8; ++j) { c1[j] = t1[j]; c2[j] = t2[j]; }
+    }
+    if (cpg >= 4) {
+      float t1[8], t2[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c1[j] = t1[j]; c2[j] = t2[j]; }
-      }
-      if (cpg >= 4) {
-        float t1[8], t2[8];
+      for (int j = 0; j < 8; ++j) { t1[j] = c1[j] + c1[j ^ 2]; t2[j] = c2[j] + c2[j ^ 2]; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { t1[j] = c1[j] + c1[j ^ 2]; t2[j] = c2[j] + c2[j ^ 2]; }
+      for (int j = 0; j < 8; ++j) { c1[j] = t1[j]; c2[j] = t2[j]; }
+    }
+    if (cpg >= 8) {
+      float t1[8], t2[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c1[j] = t1[j]; c2[j] = t2[j]; }
-      }
-      if (cpg >= 8) {
-        float t1[8], t2[8];
+      for (int j = 0; j < 8; ++j) { t1[j] = c1[j] + c1[j ^ 4]; t2[j] = c2[j] + c2[j ^ 4]; }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { t1[j] = c1[j] + c1[j ^ 4]; t2[j] = c2[j] + c2[j ^ 4]; }
+      for (int j = 0; j < 8; ++j) { c1[j] = t1[j]; c2[j] = t2[j]; }
+    }
+    for (int o = 1; o < cpg / 8; o <<= 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { c1[j] = t1[j]; c2[j] = t2[j]; }
-      }
-      for (int o = 1; o < cpg / 8; o <<= 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { c1[j] += __shfl_xor_sync(0xffffffffu, c1[j], o); c2[j] += __shfl_xor_sync(0xffffffffu, c2[j], o); }
-      }
-      const float4 g0 = *reinterpret_cast<const float4*>(s_ga + seg * 8), g1 = *reinterpret_cast<const float4*>(s_ga + seg * 8 + 4);
-      const float4 e0 = *reinterpret_cast<const float4*>(s_be + seg * 8), e1 = *reinterpret_cast<const float4*>(s_be + seg * 8 + 4);
+      for (int j = 0; j < 8; ++j) { c1[j] += __shfl_xor_sync(0xffffffffu, c1[j], o); c2[j] += __shfl_xor_sync(0xffffffffu, c2[j], o); }
+    }
+    if (lane < 8) {
+      const float4 g0 = *reinterpret_cast<const float4*>(s_ga + sseg * 8), g1 = *reinterpret_cast<const float4*>(s_ga + sseg * 8 + 4);
+      const float4 e0 = *reinterpret_cast<const float4*>(s_be + sseg * 8), e1 = *reinterpret_cast<const float4*>(s_be + sseg * 8 + 4);
       const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float be[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
       float ca[8], cb[8];
@@ -307,11 +281,39 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
         ca[j] = ga[j] * rsqrtf(var + eps);
         cb[j] = fmaf(-mean, ca[j], be[j]);
       }
+      float4* da = reinterpret_cast<float4*>(s_ab + sseg * 8);
+      float4* db = reinterpret_cast<float4*>(s_ab + C + sseg * 8);
+      da[0] = make_float4(ca[0], ca[1], ca[2], ca[3]); da[1] = make_float4(ca[4], ca[5], ca[6], ca[7]);
+      db[0] = make_float4(cb[0], cb[1], cb[2], cb[3]); db[1] = make_float4(cb[4], cb[5], cb[6], cb[7]);
+    }
+  };
+  const bool stats_async = warp == 3 && !warp_ok;  // warp 3 holds no token: its statistics overlap the sample before
+  if (warp == 3 && b0 < B2) sample_stats();
+#ifdef RD_TCA_PROF
+  long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_last = clock64();
+  int nsamp = 0;
+#endif
+
+  for (int b = b0; b < B2; b += bstep) {
+    if (warp != 3) {  // (warp 3 waited for these rows when it formed their statistics)
+      mbar_wait(bar_x, xpar);  // this sample's rows have landed
+      xpar ^= 1;
+    }
+    TCA_MARK(0);
+    pipe_sync();  // the affine table of this sample is complete
+    TCA_MARK(1);
+    // ---- GroupNorm: y = x a + b with the per-channel (a, b) of this sample; thread = 8-channel segment of rows rsub, rsub + 16, ...
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(s_ab + seg * 8), a1 = *reinterpret_cast<const float4*>(s_ab + seg * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(s_ab + C + seg * 8), b1 = *reinterpret_cast<const float4*>(s_ab + C + seg * 8 + 4);
+      const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int k = 0; k < T16; ++k) {
         const int row = rsub + 16 * k;
         if (row < T) {
-          const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+          const uint4 raw = *reinterpret_cast<const uint4*>(Stg + row * 128 + seg * 16);
+          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
           uint32_t o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -396,7 +398,9 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
     product_done();
     TCA_MARK(7);
     // the keys are consumed: their image is the landing buffer of the next sample's rows
-    if (r == 0 && b + bstep < B2) prefetch(b + bstep);
+    const bool more = b + bstep < B2;
+    if (r == 0 && more) prefetch(b + bstep);
+    if (warp == 3 && !stats_async && more) sample_stats();  // (T > 96: warp 3 has query rows of its own, no overlap)
 
     // ---- softmax_j(scale * s_ij) over the T valid keys of this thread's row: maximum on the raw scores (scale > 0),
     // exp(scale (s - m)) as one FMA + ex2; the row sum (of the unrounded values) divides Y in the epilogue
@@ -426,7 +430,16 @@ __global__ void __launch_bounds__(128 * TcLayout<T16>::NP, 1)
         }
       }
     }
-    operands_ready();
+    if (stats_async) {
+      // hand over without waiting (this warp wrote no operand), then the next sample's statistics while the others run
+      // the last product and the epilogue; the table is published by the pipeline barrier at the top of the next sample
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      asm volatile("bar.arrive %0, 128;" ::"r"(1 + pipe) : "memory");
+      if (more) sample_stats();
+    } else {
+      operands_ready();
+    }
     TCA_MARK(8);
     if (r == 0) {
       tc_fence_after_sync();
