@@ -102,33 +102,50 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_begin, self.continued = [], None, index, None, False
 
     def start(self):
+        """Starts the poller (call it BEFORE the warm-up: nvidia-smi needs a few hundred ms to print its first row, longer
+        than a 20-iteration timed region); rows are stamped with their arrival time."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def begin(self):
+        """The timed region starts now: only rows that arrive from here on are reported."""
+        self.t_begin = time.time()
+
+    def rows_in_region(self):
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        return sum(1 for t, _ in self.rows if t >= t0)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        t_end = time.time()
+        time.sleep(0.15)   # a row sampled under load just before the end is still in the pipe
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        rows = [r for t, r in self.rows if t0 <= t <= t_end + 0.15]
+        window = "timed region" if not self.continued else "same load continued untimed until the first nvidia-smi row (region shorter than the polling period)"
+        if not rows and self.rows:   # region shorter than the polling period: the row closest to it (the warm-up runs the same load)
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - t0))[1]]
+            window = "closest sample to the timed region (warm-up, same load)"
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
         busy = [v for v in sm if v > 0.5 * (max(mx) if mx else 1)] or sm
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def static_config(B, world):
@@ -382,15 +399,16 @@ def main():
         return eng.sample(x0, labels, weight, seed=seed, use_graph=True, n_iter=n, start_step=start)
 
     # ---- warm-up (also builds and instantiates the CUDA graph)
+    clocks = ClockSampler(local_rank)
+    clocks.start()   # polling from before the warm-up; only rows from the timed region are reported
     run_iters(args.warmup)
     torch.cuda.synchronize(dev)
     # ---- timed region: exactly K iterations, CUDA events on the engine's stream, barrier + sync on both sides
     K = args.steps
-    clocks = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    clocks.start()
+    clocks.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     done = 0
     e0.record(torch.cuda.current_stream(dev))
@@ -402,8 +420,15 @@ def main():
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    clk = clocks.stop()
     ms_total = e0.elapsed_time(e1)
+    # a timed region shorter than nvidia-smi's polling period has no clock row yet: keep the SAME load running (untimed)
+    # until one arrives, so that the reported clocks are clocks under this load
+    t_wait = time.time()
+    while clocks.proc is not None and clocks.rows_in_region() == 0 and time.time() - t_wait < 2.0:
+        run_iters(min(5, ITERS_PER_PASS))
+        torch.cuda.synchronize(dev)
+        clocks.continued = True
+    clk = clocks.stop()
     inside = bool(cube.inside(xs).all())
     # final all-gather (once per sampler pass)
     ag_ms = 0.0
