@@ -143,6 +143,25 @@ def test_conv_launch_geometry_invariants():
         assert 0 < smem.value <= 227 * 1024 - 2048
         assert 1 <= grid.value <= 148
         assert rows.value % 2 == 1 and rows.value >= 128
+    # stride-2 (Downsample) launches: polyphase layout, four parity planes per operand stage.  The plain-gather transform
+    # stages chunk i+1 before it reports chunk i, so these launches need two operand stages; a tile must hold at least one
+    # sample's (Ho+1) x (Wo+1) positions
+    for c0, cout, H, W in [(64, 64, 8, 9), (128, 128, 4, 4), (64, 64, 9, 9), (64, 64, 12, 10), (256, 128, 16, 16), (512, 128, 8, 8),
+                           (512, 128, 4, 4), (64, 64, 6, 7)]:
+        op = D.OpConv()
+        op.nsrc = 1
+        op.src[0].ptr, op.src[0].C, op.src[0].Hs, op.src[0].Ws = 0x1000, c0, H, W
+        op.H_in, op.W_in, op.H_out, op.W_out = H, W, (H - 2) // 2 + 1, (W - 2) // 2 + 1
+        op.pad, op.stride, op.ntaps, op.C_out = 0, 2, 9, cout
+        op.w, op.bias, op.out, op.out_scale, op.B2 = 0x1000, 0x1000, 0x1000, 1.0, 16384
+        geom = (C.c_int * 12)()
+        assert lib.rd_conv_geometry(C.byref(op), geom) == 0, lib.rd_last_error()
+        S, nt, R, n_groups, a_stages, w_res, w_stages, acc, xmode, smem, grid, tmem = list(geom)
+        assert 0 < smem <= 227 * 1024 - 2048 and 1 <= grid <= 148 and R % 2 == 1
+        assert a_stages >= 2 and xmode == 0
+        assert S >= 1 and S * (op.H_out + 1) * (op.W_out + 1) <= nt * 128     # whole samples per group of accumulator tiles
+        assert R >= 4 * nt * 128                                               # four parity planes of nt tiles each
+        assert n_groups == (16384 + S - 1) // S and tmem in (32, 64, 128, 256, 512)
     bad = D.OpConv()
     bad.nsrc, bad.ntaps = 1, 5
     assert lib.rd_conv_launch_info(C.byref(bad), None, None, None) != 0 and b"ntaps" in lib.rd_last_error()
