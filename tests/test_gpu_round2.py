@@ -431,6 +431,7 @@ from models import utils as mutils
 from oracle import rd_oracle as O
 from helpers import make_config, oracle_cfg
 isz, scale_by_sigma = int(sys.argv[4]), bool(int(sys.argv[5]))
+torch.backends.cudnn.allow_tf32 = False
 torch.manual_seed(0)
 cfg = make_config(isz, isz, "langevin", scale_by_sigma=scale_by_sigma)
 sd = O.synth_state_dict(oracle_cfg(isz, isz, scale_by_sigma=scale_by_sigma), seed=7, out_scale=1.0)
@@ -469,3 +470,27 @@ def test_out_head_mma_matches_general_kernel(tmp_path, isz, scale_by_sigma):
     assert torch.isfinite(a).all() and a.abs().max() > 0
     err = float((a - b).abs().max() / b.abs().max())
     assert err <= 5e-5, f"mma output head deviates from the general kernel: {err:.3e} of max"
+
+
+@pytest.mark.parametrize("isz", [8, 9])
+def test_polyphase_stride2_matches_one_plane_layout(tmp_path, isz):
+    """Downsample convolutions (layerspp.py:157-159) on the polyphase operand layout (four parity planes, accumulator rows =
+    output positions) against the one-plane layout that computes every input position (RD_CONV_POLY=0, read once per
+    process -> two subprocesses).  Both issue the same products in the same (chunk, tap, k-step) order into fp32 TMEM
+    accumulators, so the guided score of the whole network must be bit-identical."""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    outs = []
+    for flag in ("1", "0"):
+        out = str(tmp_path / f"score_poly_{flag}.pt")
+        env = dict(os.environ, RD_CONV_POLY=flag)
+        r = subprocess.run([sys.executable, "-c", _HEAD_SCRIPT, root, os.path.join(root, "optimized-diffusion-model_b200"), here,
+                            str(isz), "0", out], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(out))
+    a, b = outs
+    assert torch.isfinite(a).all() and a.abs().max() > 0
+    diff = float((a - b).abs().max())
+    print(f"polyphase vs one-plane stride-2 layout at {isz}x9: max |diff| = {diff:.3e}")
+    assert diff == 0.0
